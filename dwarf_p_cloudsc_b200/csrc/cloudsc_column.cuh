@@ -1,0 +1,804 @@
+/*
+ * cloudsc_column.cuh -- CLOUDSC for ONE column as a single fused top-to-bottom sweep.
+ *
+ * This is the arithmetic of the reference kernel src/cloudsc_c/cloudsc/cloudsc_c.c:360-2582
+ * (dwarf-cloudsc-c) re-organised for one GPU thread per column:
+ *
+ *  - ONE loop over the klev levels.  The reference makes ~10 passes over [klev][klon] temporaries
+ *    (init :462-513, tidy-up :519-575, saturation :583-640, sweep :732-2508, fluxes :2521-2582,
+ *    ~51 KB of stack per column); here every such temporary is a scalar of the current level and
+ *    the only state that survives from level k-1 to k is `struct Carry` below.
+ *  - the 5x5 source/sink matrices are fully unrolled register arrays; entries that no process ever
+ *    writes stay compile-time zeros, and the implicit solve uses the fact that with the shipped
+ *    process set (iwarmrain=2) ZSOLQB has only the entries (l,l) (i,i) (l,s) (i,s), so the
+ *    non-pivoting LU of :2351-2397 collapses to two multipliers and five divides (derivation at
+ *    `solve` below; value-identical to the full elimination, signs of zeros aside).
+ *  - every output element is written exactly once (the reference read-modify-writes the
+ *    tendencies, :526-567 then :2465-2498, and re-reads the flux sums, :2548-2568).
+ *  - parameters come from `CloudscConst<T>` (constant memory on the device).
+ *
+ * Floating-point evaluation order follows the reference statement by statement (comments give
+ * the cloudsc_c.c line), so that a host build of this header with contraction disabled is
+ * bit-identical to the reference on the same inputs (tests/host_emul) and the GPU build differs
+ * only by FMA contraction and the CUDA libm.
+ *
+ * The code is generic over the arithmetic type T (double, float) and over an IO policy that
+ * provides level-indexed loads/stores (plain global memory, or the TMA-staged shared-memory
+ * pipeline in cloudsc_kernels.cu).  Physics switches are specialised on the values the reference
+ * hard-codes (cloudsc_c.c:367-382: iwarmrain=2, ievaprain=2, ievapsnow=1, idepice=1) and on
+ * laer*=false; cloudsc_b200_set_params() refuses any other parameter set.
+ */
+#ifndef CLOUDSC_COLUMN_CUH
+#define CLOUDSC_COLUMN_CUH
+
+#include "cloudsc_consts.h"
+
+#if defined(__CUDACC__)
+#define CLOUDSC_FN __device__ __forceinline__
+#else
+#include <cmath>
+#define CLOUDSC_FN static inline
+#endif
+
+namespace cloudsc {
+
+/* ---- input / output slots the IO policy understands ----------------------------------------- */
+enum InSlot {
+  IN_PT, IN_PQ, IN_TT, IN_TQ, IN_TA, IN_PA, IN_PAP, IN_PSUPSAT, IN_PLUDE, IN_PLU, IN_PSNDE,
+  IN_PMFU, IN_PMFD, IN_PHRSW, IN_PHRLW, IN_PVERVEL, IN_PVFL, IN_PVFI,
+  IN_PCLV0, IN_PCLV1, IN_PCLV2, IN_PCLV3, IN_TCLD0, IN_TCLD1, IN_TCLD2, IN_TCLD3,
+  IN_PAPH, /* [klev+1] */
+  N_IN
+};
+enum OutSlot {
+  OUT_TT, OUT_TQ, OUT_TA, OUT_TCLD0, OUT_TCLD1, OUT_TCLD2, OUT_TCLD3, OUT_TCLD4, OUT_COVPTOT,
+  OUT_PLUDE,
+  /* [klev+1] flux rows */
+  OUT_FSQLF, OUT_FSQIF, OUT_FCQNNG, OUT_FCQLNG, OUT_FSQRF, OUT_FSQSF, OUT_FCQRNG, OUT_FCQSNG,
+  OUT_FSQLTUR, OUT_FSQITUR, OUT_FPLSL, OUT_FPLSN, OUT_FHPSL, OUT_FHPSN,
+  N_OUT
+};
+
+/* ---- math wrappers: same names for double/float, host/device -------------------------------- */
+template <typename T> CLOUDSC_FN T mx(T a, T b) { return fmax(a, b); }
+template <typename T> CLOUDSC_FN T mn(T a, T b) { return fmin(a, b); }
+#if defined(__CUDACC__)
+CLOUDSC_FN double ex(double x) { return exp(x); }
+CLOUDSC_FN float ex(float x) { return expf(x); }
+CLOUDSC_FN double pw(double x, double y) { return pow(x, y); }
+CLOUDSC_FN float pw(float x, float y) { return powf(x, y); }
+CLOUDSC_FN double sq(double x) { return sqrt(x); }
+CLOUDSC_FN float sq(float x) { return sqrtf(x); }
+CLOUDSC_FN double ab(double x) { return fabs(x); }
+CLOUDSC_FN float ab(float x) { return fabsf(x); }
+CLOUDSC_FN double cs(double x, double y) { return copysign(x, y); }
+CLOUDSC_FN float cs(float x, float y) { return copysignf(x, y); }
+#else
+static inline double ex(double x) { return std::exp(x); }
+static inline float ex(float x) { return std::exp(x); }
+static inline double pw(double x, double y) { return std::pow(x, y); }
+static inline float pw(float x, float y) { return std::pow(x, y); }
+static inline double sq(double x) { return std::sqrt(x); }
+static inline float sq(float x) { return std::sqrt(x); }
+static inline double ab(double x) { return std::fabs(x); }
+static inline float ab(float x) { return std::fabs(x); }
+static inline double cs(double x, double y) { return std::copysign(x, y); }
+static inline float cs(float x, float y) { return std::copysign(x, y); }
+#endif
+
+/* State carried from level k-1 to level k (what "k-caching" keeps in registers) */
+template <typename T>
+struct Carry {
+  T tp1_m1;      /* ztp1[jk-1]            cloudsc_c.c:1025,1868 */
+  T a_m1;        /* za[jk-1] (clamped)    :1390,1597 */
+  T pap_m1;      /* pap[jk-1]             :1026 */
+  T paph_k;      /* paph[jk]              :803 */
+  T mf_k;        /* pmfu[jk]+pmfd[jk]     :1005,1146 */
+  T anewm1;      /* zanewm1               :2179 -> :1006,1027 */
+  T qlnm1, qinm1;/* zqxnm1[l], zqxnm1[i]  :2419 -> :1013 */
+  T pf_i, pf_r, pf_s; /* zpfplsx[i,r,s][jk] :2432 -> :1550 (liquid/vapour components are 0) */
+  T covptot, covpmax; /* :1597-1608 */
+  T cldtopdist;  /* :1390-1395 */
+  T rainfrac;    /* prainfrac_toprfz :1875 -> :1881 */
+  T fsqlf, fsqif, fcqlng, fcqnng, fsqltur, fsqitur; /* running flux sums :2548-2568 */
+};
+
+/* FOEALFA / FOEEWM pieces (cloudsc_c.c:335-351, inlined by the reference at every use) */
+template <typename T>
+CLOUDSC_FN T foealfa(const CloudscConst<T> &c, T t) {
+  const T x = (mx(c.rtice, mn(c.rtwat, t)) - c.rtice) * c.rtwat_rtice_r;
+  return mn(T(1.0), x * x);
+}
+template <typename T>
+CLOUDSC_FN T exp_liq(const CloudscConst<T> &c, T t) { return ex((c.r3les * (t - c.rtt)) / (t - c.r4les)); }
+template <typename T>
+CLOUDSC_FN T exp_ice(const CloudscConst<T> &c, T t) { return ex((c.r3ies * (t - c.rtt)) / (t - c.r4ies)); }
+template <typename T>
+CLOUDSC_FN T foedem(const CloudscConst<T> &c, T t, T al) {
+  const T dl = t - c.r4les, di = t - c.r4ies;
+  return (al * c.r5alvcp) * (T(1.0) / (dl * dl)) + ((T(1.0) - al) * c.r5alscp) * (T(1.0) / (di * di));
+}
+template <typename T>
+CLOUDSC_FN T foeldcpm(const CloudscConst<T> &c, T al) { return al * c.ralvdcp + (T(1.0) - al) * c.ralsdcp; }
+
+/*
+ * One Newton step of the saturation adjustment, cloudsc_c.c:1162-1168 (and :1169-1175).
+ */
+template <typename T>
+CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
+  const T al = foealfa(c, tn);
+  T qsat = (c.r2es * (al * exp_liq(c, tn) + (T(1.0) - al) * exp_ice(c, tn))) * qp;
+  qsat = mn(T(0.5), qsat);
+  const T cor = T(1.0) / (T(1.0) - c.retv * qsat);
+  qsat = qsat * cor;
+  const T cond = (qsm - qsat) / (T(1.0) + (qsat * cor) * foedem(c, tn, al));
+  tn = tn + foeldcpm(c, al) * cond;
+  qsm = qsm - cond;
+}
+
+/*
+ * The column sweep.  IO must provide
+ *   template<int S> T ld(int k) const;        input slot S at level k (0-based; IN_PAPH: row k)
+ *   template<int S> void st(int k, T v);      output slot S at row k
+ *   T plsm() const; int ktype() const; void st_rainfrac(T);
+ */
+template <typename T, typename IO>
+CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev, const T ptsphy) {
+  const T zero = T(0.0), one = T(1.0);
+  const T zepsec = T(1.0e-14);
+  const T zepsilon = T(100.0) * (sizeof(T) == 8 ? T(2.220446049250313e-16) : T(1.1920929e-07f)); /* :360 */
+  /* cloudsc_c.c:385-391 */
+  const T zqtmst = one / ptsphy;
+  const T zrdcp = c.rd / c.rcpd;
+  const T zrg_r = one / c.rg;
+  const T zrldcp = one / (c.ralsdcp - c.ralvdcp);
+  /* wet-bulb fit constants, cloudsc_c.c:266-270 */
+  const T ztw1 = T(1329.31), ztw2 = T(0.0074615), ztw3 = T(0.85e5), ztw4 = T(40.637), ztw5 = T(275.0);
+
+  const int ktop = c.ncldtop - 1; /* first level (0-based) of the physics sweep, :732 */
+
+  /* per-column constants */
+  const T paph_surf = io.template ld<IN_PAPH>(klev); /* paph[klev+1] :1260,2064 */
+  const T plsm = io.plsm();
+  const int ktype = io.ktype();
+  /* cloudsc_c.c:1710-1717 */
+  const bool land = plsm > T(0.5);
+  const T kk_num_pow = land ? c.kk_num_pow_land : c.kk_num_pow_sea;
+  const T lcrit_kk = land ? c.rclcrit_land : c.rclcrit_sea;
+
+  Carry<T> s;
+  s.tp1_m1 = zero; s.a_m1 = zero; s.pap_m1 = zero;
+  s.paph_k = io.template ld<IN_PAPH>(0);
+  s.mf_k = zero;
+  s.anewm1 = zero; s.qlnm1 = zero; s.qinm1 = zero;           /* :718 */
+  s.pf_i = zero; s.pf_r = zero; s.pf_s = zero;               /* :493 */
+  s.covptot = zero; s.covpmax = zero; s.cldtopdist = zero;   /* :720-723 */
+  s.rainfrac = zero;                                         /* :512 */
+  s.fsqlf = zero; s.fsqif = zero; s.fcqlng = zero; s.fcqnng = zero; s.fsqltur = zero; s.fsqitur = zero;
+
+  /* row 0 of every flux output, :2533-2542 and zpfplsx[.][0]=0 -> :2523-2524,2578-2579 */
+  io.template st<OUT_FSQLF>(0, zero);  io.template st<OUT_FSQIF>(0, zero);
+  io.template st<OUT_FSQRF>(0, zero);  io.template st<OUT_FSQSF>(0, zero);
+  io.template st<OUT_FCQLNG>(0, zero); io.template st<OUT_FCQNNG>(0, zero);
+  io.template st<OUT_FCQRNG>(0, zero); io.template st<OUT_FCQSNG>(0, zero);
+  io.template st<OUT_FSQLTUR>(0, zero); io.template st<OUT_FSQITUR>(0, zero);
+  io.template st<OUT_FPLSL>(0, zero);  io.template st<OUT_FPLSN>(0, zero);
+  io.template st<OUT_FHPSL>(0, -c.rlvtt * zero); io.template st<OUT_FHPSN>(0, -c.rlstt * zero);
+
+  for (int k = 0; k < klev; ++k) {
+    /* ================= 1. initial values of this level, :462-485 ========================== */
+    const T pap = io.template ld<IN_PAP>(k);
+    const T paph_n = io.template ld<IN_PAPH>(k + 1);
+    const T t = io.template ld<IN_PT>(k) + ptsphy * io.template ld<IN_TT>(k);
+    T qv = io.template ld<IN_PQ>(k) + ptsphy * io.template ld<IN_TQ>(k);
+    T a = io.template ld<IN_PA>(k) + ptsphy * io.template ld<IN_TA>(k);
+    const T aorig = a;
+    T qx[4], qx0[4], lneg[4];
+    qx[0] = io.template ld<IN_PCLV0>(k) + ptsphy * io.template ld<IN_TCLD0>(k);
+    qx[1] = io.template ld<IN_PCLV1>(k) + ptsphy * io.template ld<IN_TCLD1>(k);
+    qx[2] = io.template ld<IN_PCLV2>(k) + ptsphy * io.template ld<IN_TCLD2>(k);
+    qx[3] = io.template ld<IN_PCLV3>(k) + ptsphy * io.template ld<IN_TCLD3>(k);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { qx0[m] = qx[m]; lneg[m] = zero; }
+    T tend_t = zero, tend_q = zero;
+
+    /* ---- tidy up very small cloud cover / condensate, :519-541 */
+    if (qx[0] + qx[1] < c.rlmin || a < c.ramin) {
+      lneg[0] = lneg[0] + qx[0];
+      T qadj = qx[0] * zqtmst;
+      tend_q = tend_q + qadj;
+      tend_t = tend_t - c.ralvdcp * qadj;
+      qv = qv + qx[0];
+      qx[0] = zero;
+      lneg[1] = lneg[1] + qx[1];
+      qadj = qx[1] * zqtmst;
+      tend_q = tend_q + qadj;
+      tend_t = tend_t - c.ralsdcp * qadj;
+      qv = qv + qx[1];
+      qx[1] = zero;
+      a = zero;
+    }
+    /* ---- tidy up small CLV variables, :547-575 (iphase = l:1 i:2 r:1 s:2) */
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (qx[m] < c.rlmin) {
+        lneg[m] = lneg[m] + qx[m];
+        const T qadj = qx[m] * zqtmst;
+        tend_q = tend_q + qadj;
+        tend_t = tend_t - ((m & 1) ? c.ralsdcp : c.ralvdcp) * qadj;
+        qv = qv + qx[m];
+        qx[m] = zero;
+      }
+    }
+
+    /* ---- saturation values, :588-603 */
+    const T alfa_w = foealfa(c, t);                 /* zfoealfa */
+    const T e_liq = exp_liq(c, t), e_ice = exp_ice(c, t);
+    const T foeewmt = mn((c.r2es * (alfa_w * e_liq + (one - alfa_w) * e_ice)) / pap, T(0.5));
+    const T qsmix = foeewmt / (one - c.retv * foeewmt);
+    const T zalfa = mx(zero, cs(one, t - c.rtt));
+    T foeew = mn((zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice)) / pap, T(0.5));
+    foeew = mn(T(0.5), foeew);
+    const T qsice = foeew / (one - c.retv * foeew);
+    const T foeeliqt = mn((c.r2es * e_liq) / pap, T(0.5));
+    const T qsliq = foeeliqt / (one - c.retv * foeeliqt);
+    /* ---- cloud fraction in [0,1]; liquid/ice fractions, :625-636 */
+    a = mx(zero, mn(one, a));
+    const T li = qx[0] + qx[1];
+    T liqfrac = zero, icefrac = zero;
+    if (li > c.rlmin) { liqfrac = qx[0] / li; icefrac = one - liqfrac; }
+
+    /* values of this level the flux section needs (zqxn2d stays 0 above ncldtop, :503) */
+    T qxn2d[4] = {zero, zero, zero, zero};
+    T plude_out = io.template ld<IN_PLUDE>(k); /* plude[jk] as the flux section sees it, :2559 */
+    T tend_a = zero, tcld[4] = {zero, zero, zero, zero}, covptot_out = zero;
+    T pf_i_n = zero, pf_r_n = zero, pf_s_n = zero;  /* zpfplsx[.][jk+1] */
+    /* pmfu+pmfd of the level below (:1067,1143); becomes mf_k of the next iteration (needs ncldtop >= 2) */
+    const T mf_n = (k + 1 < klev && k + 1 >= ktop) ? io.template ld<IN_PMFU>(k + 1) + io.template ld<IN_PMFD>(k + 1) : zero;
+
+    if (k >= ktop) {
+      /* ================= 3.0 initialise, :739-859 ========================================= */
+      T qxfg[4] = {qx[0], qx[1], qx[2], qx[3]};
+      T qa[5][5], qb03 = zero, qb13 = zero, qb00 = zero, qb11 = zero;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) qa[i][j] = zero;
+      T solab = zero, solac = zero;
+      T convsrce0 = zero, convsrce1 = zero, psupsrce0 = zero, psupsrce1 = zero;
+      T convsink = zero; /* zconvsink[l] == zconvsink[i] */
+
+      const T dp = paph_n - s.paph_k;
+      const T gdp = c.rg / dp;
+      const T rho = pap / (c.rd * t);
+      const T dtgdp = ptsphy * gdp;
+      const T rdtgdp = dp * (one / (ptsphy * c.rg));
+      /* dqs/dT correction factors, :818-834 */
+      const T dl = t - c.r4les, di = t - c.r4ies;
+      const T facw = c.r5les / (dl * dl);
+      T cor = one / (one - c.retv * foeeliqt);
+      const T dqsliqdt = (facw * cor) * qsliq;
+      const T corqsliq = one + c.ralvdcp * dqsliqdt;
+      const T faci = c.r5ies / (di * di);
+      cor = one / (one - c.retv * foeew);
+      const T dqsicedt = (faci * cor) * qsice;
+      const T corqsice = one + c.ralsdcp * dqsicedt;
+      const T facm = alfa_w * facw + (one - alfa_w) * faci;
+      cor = one / (one - c.retv * foeewmt);
+      const T dqsmixdt = (facm * cor) * qsmix;
+      const T corqsmix = one + foeldcpm(c, alfa_w) * dqsmixdt;
+      const T evaplimmix = mx((qsmix - qv) / corqsmix, zero);
+      /* zevaplimliq (:833) is never read; zevaplimice only by the dead ievapsnow=2 branch */
+      (void)corqsliq;
+      /* in-cloud condensate, :837-840 */
+      T tmpa = one / mx(a, zepsec);
+      T liqcld = qx[0] * tmpa;
+      T icecld = qx[1] * tmpa;
+      T licld = liqcld + icecld;
+
+      /* evaporate very small amounts of liquid and ice, :847-857 */
+      if (qx[0] < c.rlmin) { qa[0][4] = qx[0]; qa[4][0] = -qx[0]; }
+      if (qx[1] < c.rlmin) { qa[1][4] = qx[1]; qa[4][1] = -qx[1]; }
+
+      /* ================= 3.1 ice supersaturation adjustment, :879-952 ===================== */
+      const T fokoop = mn(c.rkoop1 - c.rkoop2 * t, (c.r2es * e_liq) / (c.r2es * e_ice));
+      {
+        T fac, facI;
+        if (c.nssopt == 0 || t >= c.rtt) { fac = one; facI = one; }
+        else { fac = a + fokoop * (one - a); facI = ptsphy / c.rkooptau; }
+        T supsat;
+        if (a > one - c.ramin) {
+          supsat = mx((qv - fac * qsice) / corqsice, zero);
+        } else {
+          const T qp1env = (qv - a * qsice) / mx(one - a, zepsilon);
+          supsat = mx(((one - a) * (qp1env - fac * qsice)) / corqsice, zero);
+        }
+        if (supsat > zepsec) {
+          if (t > c.rthomo) { qa[4][0] = qa[4][0] + supsat; qa[0][4] = qa[0][4] - supsat; qxfg[0] = qxfg[0] + supsat; }
+          else              { qa[4][1] = qa[4][1] + supsat; qa[1][4] = qa[1][4] - supsat; qxfg[1] = qxfg[1] + supsat; }
+          solac = (one - a) * facI;
+        }
+        const T psupsat = io.template ld<IN_PSUPSAT>(k);
+        if (psupsat > zepsec) {
+          if (t > c.rthomo) { qa[0][0] = qa[0][0] + psupsat; psupsrce0 = psupsat; qxfg[0] = qxfg[0] + psupsat; }
+          else              { qa[1][1] = qa[1][1] + psupsat; psupsrce1 = psupsat; qxfg[1] = qxfg[1] + psupsat; }
+          solac = (one - a) * facI;
+        }
+      }
+
+      /* ================= 3.2 detrainment from convection, :967-987 ======================== */
+      if (k + 1 < klev) {
+        const T plu_n = io.template ld<IN_PLU>(k + 1);
+        plude_out = plude_out * dtgdp;
+        if (plu_n > zepsec && plude_out > c.rlmin) {
+          solac = solac + plude_out / plu_n;
+          convsrce0 = alfa_w * plude_out;
+          convsrce1 = (one - alfa_w) * plude_out;
+          qa[0][0] = qa[0][0] + convsrce0;
+          qa[1][1] = qa[1][1] + convsrce1;
+        } else {
+          plude_out = zero;
+        }
+        qa[3][3] = qa[3][3] + io.template ld<IN_PSNDE>(k) * dtgdp;
+        io.template st<OUT_PLUDE>(k, plude_out);
+      }
+
+      /* ================= 3.3 subsidence compensating convective updraughts, :1002-1075 ==== */
+      if (k > ktop) {
+        const T mf = mx(zero, s.mf_k * dtgdp);
+        T acust = mf * s.anewm1;
+        const T lcust0 = mf * s.qlnm1, lcust1 = mf * s.qinm1;
+        convsrce0 = convsrce0 + lcust0;
+        convsrce1 = convsrce1 + lcust1;
+        const T dtdp = ((zrdcp * T(0.5)) * (s.tp1_m1 + t)) / s.paph_k;
+        const T dtforc = dtdp * (pap - s.pap_m1);
+        const T dqs_s = (s.anewm1 * dtforc) * dqsmixdt;
+        T lfinalsum = zero;
+        {
+          T lfinal = mx(zero, lcust0 - dqs_s);
+          T evap = mn(lcust0 - lfinal, evaplimmix);
+          lfinal = lcust0 - evap;
+          lfinalsum = lfinalsum + lfinal;
+          qa[0][0] = qa[0][0] + lcust0; qa[0][4] = qa[0][4] + evap; qa[4][0] = qa[4][0] - evap;
+          lfinal = mx(zero, lcust1 - dqs_s);
+          evap = mn(lcust1 - lfinal, evaplimmix);
+          lfinal = lcust1 - evap;
+          lfinalsum = lfinalsum + lfinal;
+          qa[1][1] = qa[1][1] + lcust1; qa[1][4] = qa[1][4] + evap; qa[4][1] = qa[4][1] - evap;
+        }
+        if (lfinalsum < zepsec) acust = zero;
+        solac = solac + acust;
+      }
+      if (k + 1 < klev) { /* subsidence sink, :1064-1075 */
+        const T mfdn = mx(zero, mf_n * dtgdp);
+        solab = solab + mfdn;
+        qb00 = qb00 + mfdn;
+        qb11 = qb11 + mfdn;
+        convsink = mfdn;
+      }
+
+      /* ================= 3.4 erosion of clouds by turbulent mixing, :1087-1118 ============ */
+      {
+        T ldifdt = c.rcldiff * ptsphy;
+        if (ktype > 0 && plude_out > zepsec) ldifdt = c.rcldiff_convi * ldifdt;
+        if (li > zepsec) {
+          const T e = ldifdt * mx(qsmix - qv, zero);
+          T leros = a * e;
+          leros = mn(leros, evaplimmix);
+          leros = mn(leros, li);
+          const T aeros = leros / licld;
+          solac = solac - aeros;
+          qa[0][4] = qa[0][4] + liqfrac * leros; qa[4][0] = qa[4][0] - liqfrac * leros;
+          qa[1][4] = qa[1][4] + icefrac * leros; qa[4][1] = qa[4][1] - icefrac * leros;
+        }
+      }
+
+      /* ================= 3.4 condensation/evaporation due to dqsat/dT, :1137-1182 ========= */
+      T dqs;
+      {
+        const T dtdp = (zrdcp * t) / pap;
+        const T dpmxdt = dp * zqtmst;
+        const T mfdn = (k + 1 < klev) ? mf_n : zero;
+        T wtot = io.template ld<IN_PVERVEL>(k) + (T(0.5) * c.rg) * (s.mf_k + mfdn);
+        wtot = mn(dpmxdt, mx(-dpmxdt, wtot));
+        const T zzzdt = io.template ld<IN_PHRSW>(k) + io.template ld<IN_PHRLW>(k);
+        const T dtdiab = mn(dpmxdt * dtdp, mx(-dpmxdt * dtdp, zzzdt)) * ptsphy; /* + ralfdcp*zldefr, zldefr == 0 */
+        const T dtforc = (dtdp * wtot) * ptsphy + dtdiab;
+        T tn = t + dtforc;
+        tn = mx(tn, T(160.0));
+        const T qp = one / pap;
+        T qsm = qsmix;
+        satadj_step(c, qp, tn, qsm);
+        satadj_step(c, qp, tn, qsm);
+        dqs = qsm - qsmix;
+      }
+      /* 3.4a evaporation of clouds, :1191-1205 */
+      if (dqs > zero) {
+        T levap = a * mn(dqs, licld);
+        levap = mn(levap, evaplimmix);
+        levap = mn(levap, mx(qsmix - qv, zero));
+        qa[0][4] = qa[0][4] + liqfrac * levap; qa[4][0] = qa[4][0] - liqfrac * levap;
+        qa[1][4] = qa[1][4] + icefrac * levap; qa[4][1] = qa[4][1] - icefrac * levap;
+      }
+      /* 3.4b (1) increase of cloud water in existing clouds, :1214-1248 */
+      if (dqs <= -c.rlmin && a > zepsec) {
+        T lcond1 = mx(-dqs, zero);
+        T cdmax;
+        if (a > T(0.99)) {
+          const T corm = one / (one - c.retv * qsmix);
+          cdmax = (qv - qsmix) / (one + (corm * qsmix) * foedem(c, t, alfa_w));
+        } else {
+          cdmax = (qv - a * qsmix) / a;
+        }
+        lcond1 = mx(mn(lcond1, cdmax), zero);
+        lcond1 = a * lcond1;
+        if (lcond1 < c.rlmin) lcond1 = zero;
+        if (t > c.rthomo) { qa[4][0] = qa[4][0] + lcond1; qa[0][4] = qa[0][4] - lcond1; qxfg[0] = qxfg[0] + lcond1; }
+        else              { qa[4][1] = qa[4][1] + lcond1; qa[1][4] = qa[1][4] - lcond1; qxfg[1] = qxfg[1] + lcond1; }
+      }
+      /* 3.4b (2) generation of new clouds, :1254-1361 */
+      if (dqs <= -c.rlmin && a < one - zepsec) {
+        T rhc = c.ramid;
+        const T sigk = pap / paph_surf;
+        if (sigk > T(0.8)) { const T x = (sigk - T(0.8)) / T(0.2); rhc = c.ramid + (one - c.ramid) * (x * x); }
+        T qe;
+        if (c.nssopt == 0 || c.nssopt == 1) {
+          qe = (qv - a * qsice) / mx(zepsec, one - a);
+          qe = mx(zero, qe);
+        } else if (c.nssopt == 2) {
+          qe = qv;
+        } else {
+          qe = qv + li;
+        }
+        const T fac = (c.nssopt == 0 || t >= c.rtt) ? one : fokoop;
+        if (qe >= qsice * fac * rhc && qe < qsice * fac) {
+          T acond = (-((one - a) * fac) * dqs) / mx(T(2.0) * (fac * qsice - qe), zepsec);
+          acond = mn(acond, one - a);
+          T lcond2 = (-(fac * dqs) * T(0.5)) * acond;
+          const T zdl = (T(2.0) * (fac * qsice - qe)) / mx(zepsec, one - a);
+          if (dqs * fac < -zdl) {
+            const T lcondlim = ((a - one) * fac) * dqs - fac * qsice + qv;
+            lcond2 = mn(lcond2, lcondlim);
+          }
+          lcond2 = mx(lcond2, zero);
+          if (one - a < zepsec || lcond2 < c.rlmin) { lcond2 = zero; acond = zero; }
+          if (lcond2 == zero) acond = zero;
+          solac = solac + acond;
+          if (t > c.rthomo) { qa[4][0] = qa[4][0] + lcond2; qa[0][4] = qa[0][4] - lcond2; qxfg[0] = qxfg[0] + lcond2; }
+          else              { qa[4][1] = qa[4][1] + lcond2; qa[1][4] = qa[1][4] - lcond2; qxfg[1] = qxfg[1] + lcond2; }
+        }
+      }
+
+      /* ================= 3.7 growth of ice by vapour deposition (Rotstayn), :1384-1447 ==== */
+      if (a >= c.rcldtopcf && s.a_m1 < c.rcldtopcf) s.cldtopdist = zero;
+      else s.cldtopdist = s.cldtopdist + dp / (rho * c.rg);
+      if (qxfg[0] > c.rlmin && t < c.rtt) {
+        const T vpice = ((c.r2es * e_ice) * c.rv) / c.rd;
+        const T vpliq = vpice * fokoop;
+        const T icenuclei = T(1000.0) * ex((T(12.96) * (vpliq - vpice)) / vpliq - T(0.639));
+        const T add = (c.rlstt * (c.rlstt / (c.rv * t) - one)) / (T(0.024) * t);
+        const T bdd = ((c.rv * t) * pap) / (T(2.21) * vpice);
+        const T cvds = ((T(7.8) * pw(icenuclei / rho, T(0.666))) * (vpliq - vpice)) / ((T(8.87) * (add + bdd)) * vpice);
+        const T ice0 = mx(icecld, (icenuclei * c.riceinit) / rho);
+        const T inew = pw((T(0.666) * cvds) * ptsphy + pw(ice0, T(0.666)), T(1.5));
+        T depos = mx(a * (inew - ice0), zero);
+        depos = mn(depos, qxfg[0]);
+        const T infactor = mn(icenuclei / T(15000.0), one);
+        depos = depos * mn(infactor + (one - infactor) * (c.rdepliqrefrate + s.cldtopdist / c.rdepliqrefdepth), one);
+        qa[0][1] = qa[0][1] + depos; qa[1][0] = qa[1][0] - depos;
+        qxfg[1] = qxfg[1] + depos; qxfg[0] = qxfg[0] - depos;
+      }
+
+      /* ================= 4. precipitation processes ====================================== */
+      tmpa = one / mx(a, zepsec);                      /* :1529-1532 */
+      liqcld = qxfg[0] * tmpa;
+      icecld = qxfg[1] * tmpa;
+      licld = liqcld + icecld;
+      (void)licld;
+
+      /* 4.2 sedimentation, :1541-1576 (species i, r, s; llfall = r,s plus ice) */
+      T qpretot = zero;
+      T fallsrce1 = zero, fallsrce2 = zero, fallsrce3 = zero;
+      if (k > ktop) {
+        fallsrce1 = s.pf_i * dtgdp; qa[1][1] = qa[1][1] + fallsrce1; qxfg[1] = qxfg[1] + fallsrce1; qpretot = qpretot + qxfg[1];
+        fallsrce2 = s.pf_r * dtgdp; qa[2][2] = qa[2][2] + fallsrce2; qxfg[2] = qxfg[2] + fallsrce2; qpretot = qpretot + qxfg[2];
+        fallsrce3 = s.pf_s * dtgdp; qa[3][3] = qa[3][3] + fallsrce3; qxfg[3] = qxfg[3] + fallsrce3; qpretot = qpretot + qxfg[3];
+      }
+      const T fallsink1 = dtgdp * (c.rvice * rho);
+      const T fallsink2 = dtgdp * (c.rvrain * rho);
+      const T fallsink3 = dtgdp * (c.rvsnow * rho);
+
+      /* precipitation cover, max-random overlap, :1595-1609 */
+      T covpclr, raincld, snowcld;
+      if (qpretot > zepsec) {
+        s.covptot = one - ((one - s.covptot) * (one - mx(a, s.a_m1))) / (one - mn(s.a_m1, one - T(1.0e-6)));
+        s.covptot = mx(s.covptot, c.rcovpmin);
+        covpclr = mx(zero, s.covptot - a);
+        raincld = qxfg[2] / s.covptot;
+        snowcld = qxfg[3] / s.covptot;
+        s.covpmax = mx(s.covptot, s.covpmax);
+      } else {
+        raincld = zero; snowcld = zero; s.covptot = zero; covpclr = zero; s.covpmax = zero;
+      }
+
+      /* 4.3a autoconversion to snow, :1617-1637 */
+      if (t <= c.rtt) {
+        if (icecld > zepsec) {
+          const T zco = (ptsphy * c.rsnowlin1) * ex(c.rsnowlin2 * (t - c.rtt));
+          const T x = icecld / c.rlcritsnow;
+          const T snowaut = zco * (one - ex(-(x * x)));
+          qb13 = qb13 + snowaut;
+        }
+      }
+      /* 4.3b warm-rain autoconversion + accretion, Khairoutdinov-Kogan, :1644-1759 */
+      if (liqcld > zepsec) {
+        T rainaut, rainacc;
+        if (liqcld > lcrit_kk) {
+          rainaut = ((((T(1.5) * a) * ptsphy) * c.rcl_kkaau) * pw(liqcld, c.rcl_kkbauq)) * kk_num_pow;
+          rainaut = mn(rainaut, qxfg[0]);
+          if (rainaut < zepsec) rainaut = zero;
+          rainacc = (((T(2.0) * a) * ptsphy) * c.rcl_kkaac) * pw(liqcld * raincld, c.rcl_kkbac);
+          rainacc = mn(rainacc, qxfg[0]);
+          if (rainacc < zepsec) rainacc = zero;
+        } else {
+          rainaut = zero; rainacc = zero;
+        }
+        if (t <= c.rtt) {
+          qa[0][3] = qa[0][3] + rainaut; qa[0][3] = qa[0][3] + rainacc;
+          qa[3][0] = qa[3][0] - rainaut; qa[3][0] = qa[3][0] - rainacc;
+        } else {
+          qa[0][2] = qa[0][2] + rainaut; qa[0][2] = qa[0][2] + rainacc;
+          qa[2][0] = qa[2][0] - rainaut; qa[2][0] = qa[2][0] - rainacc;
+        }
+      }
+      /* riming of snow by cloud water, :1771-1785 */
+      if (t <= c.rtt && liqcld > zepsec) {
+        if (s.covptot > T(0.01) && snowcld > zepsec) {
+          const T fallcorr = pw(c.rdensref / rho, T(0.4));
+          T snowrime = ((((T(0.3) * s.covptot) * ptsphy) * c.rcl_const7s) * fallcorr) *
+                       pw((rho * snowcld) * c.rcl_const1s, c.rcl_const8s);
+          snowrime = mn(snowrime, one);
+          qb03 = qb03 + snowrime;
+        }
+      }
+
+      /* 4.4a melting of snow and ice, :1817-1859 (imelt: ice->rain, snow->rain) */
+      {
+        const T icetot = qxfg[1] + qxfg[3];
+        T meltmax = zero;
+        if (icetot > zepsec && t > c.rtt) {
+          const T subsat = mx(qsice - qv, zero);
+          const T tdmtw0 = t - c.rtt - subsat * (ztw1 + ztw2 * (pap - ztw3) - ztw4 * (t - ztw5));
+          const T cons1 = ab((ptsphy * (one + T(0.5) * tdmtw0)) / c.rtaumel);
+          meltmax = mx((tdmtw0 * cons1) * zrldcp, zero);
+        }
+        if (icetot > zepsec && meltmax > zepsec) {
+          T alfa = qxfg[1] / icetot;
+          T melt = mn(qxfg[1], alfa * meltmax);
+          qxfg[1] = qxfg[1] - melt; qxfg[2] = qxfg[2] + melt;
+          qa[1][2] = qa[1][2] + melt; qa[2][1] = qa[2][1] - melt;
+          alfa = qxfg[3] / icetot;
+          melt = mn(qxfg[3], alfa * meltmax);
+          qxfg[3] = qxfg[3] - melt; qxfg[2] = qxfg[2] + melt;
+          qa[3][2] = qa[3][2] + melt; qa[2][3] = qa[2][3] - melt;
+        }
+      }
+      /* 4.4b freezing of rain, :1866-1906 */
+      if (qx[2] > zepsec) {
+        if (t <= c.rtt && s.tp1_m1 > c.rtt) {
+          const T qpre = mx(qx[3] + qx[2], zepsec);
+          s.rainfrac = qx[2] / qpre;
+        }
+        if (t < c.rtt) {
+          T frzmax;
+          if (s.rainfrac > T(0.8)) {
+            const T lambda = pw(c.rcl_fac1 / (rho * qx[2]), c.rcl_fac2);
+            const T temp = c.rcl_fzrab * (t - c.rtt);
+            const T frz = ((ptsphy * (c.rcl_const5r / rho)) * (ex(temp) - one)) * pw(lambda, c.rcl_const6r);
+            frzmax = mx(frz, zero);
+          } else {
+            const T cons1 = ab((ptsphy * (one + T(0.5) * (c.rtt - t))) / c.rtaumel);
+            frzmax = mx(((c.rtt - t) * cons1) * zrldcp, zero);
+          }
+          if (frzmax > zepsec) {
+            const T frz = mn(qx[2], frzmax);
+            qa[2][3] = qa[2][3] + frz; qa[3][2] = qa[3][2] - frz;
+          }
+        }
+      }
+      /* 4.4c freezing of liquid, :1913-1928 */
+      {
+        const T frzmax = mx((c.rthomo - t) * zrldcp, zero);
+        if (frzmax > zepsec && qxfg[0] > zepsec) {
+          const T frz = mn(qxfg[0], frzmax);
+          qa[0][1] = qa[0][1] + frz; qa[1][0] = qa[1][0] - frz;
+        }
+      }
+      /* 4.5 evaporation of rain, Abel & Boutle, :1984-2038 */
+      {
+        T zzrh = c.rprecrhmax + ((one - c.rprecrhmax) * s.covpmax) / mx(zepsec, one - a);
+        zzrh = mn(mx(zzrh, c.rprecrhmax), one);
+        zzrh = mn(T(0.8), zzrh);
+        const T qe = mx(zero, mn(qv, qsliq));
+        if (covpclr > zepsec && qxfg[2] > zepsec && qe < zzrh * qsliq) {
+          const T preclr = qxfg[2] / s.covptot;
+          const T fallcorr = pw(c.rdensref / rho, T(0.4));
+          const T esatliq = (c.rv / c.rd) * (c.r2es * e_liq);
+          const T lambda = pw(c.rcl_fac1 / (rho * preclr), c.rcl_fac2);
+          const T evap_denom = c.rcl_cdenom1 * esatliq - c.rcl_cdenom2 * t * esatliq + (c.rcl_cdenom3 * pw(t, T(3.0))) * pap;
+          const T corr2 = (pw(t / T(273.0), T(1.5)) * T(393.0)) / (t + T(120.0));
+          const T subsat = mx(zzrh * qsliq - qe, zero);
+          const T beta = (((((T(0.5) / qsliq) * (t * t)) * esatliq) * c.rcl_const1r) * (corr2 / evap_denom)) *
+                         (T(0.78) / pw(lambda, c.rcl_const4r) +
+                          (c.rcl_const2r * sq(rho * fallcorr)) / (sq(corr2) * pw(lambda, c.rcl_const3r)));
+          const T denom = one + beta * ptsphy;
+          const T dpevap = (((covpclr * beta) * ptsphy) * subsat) / denom;
+          const T evap = mn(dpevap, qxfg[2]);
+          qa[2][4] = qa[2][4] + evap; qa[4][2] = qa[4][2] - evap;
+          s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, ((s.covptot - a) * evap) / qxfg[2]));
+          qxfg[2] = qxfg[2] - evap;
+        }
+      }
+      /* 4.5 evaporation of snow, Sundqvist-type, :2050-2087 */
+      {
+        T zzrh = c.rprecrhmax + ((one - c.rprecrhmax) * s.covpmax) / mx(zepsec, one - a);
+        zzrh = mn(mx(zzrh, c.rprecrhmax), one);
+        T qe = (qv - a * qsice) / mx(zepsec, one - a);
+        qe = mx(zero, mn(qe, qsice));
+        if (covpclr > zepsec && qxfg[3] > zepsec && qe < zzrh * qsice) {
+          const T cd = s.covptot * dtgdp;
+          const T preclr = (qxfg[3] * covpclr) / cs(mx(ab(cd), zepsilon), cd);
+          const T beta1 = ((sq(pap / paph_surf) / c.rvrfactor) * preclr) / mx(covpclr, zepsec);
+          const T beta = (c.rg * c.rpecons) * pw(beta1, T(0.5777));
+          const T denom = one + (beta * ptsphy) * corqsice;
+          const T dpr = ((((covpclr * beta) * (qsice - qe)) / denom) * dp) * zrg_r;
+          const T dpevap = dpr * dtgdp;
+          const T evap = mn(dpevap, qxfg[3]);
+          qa[3][4] = qa[3][4] + evap; qa[4][3] = qa[4][3] - evap;
+          s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, ((s.covptot - a) * evap) / qxfg[3]));
+          qxfg[3] = qxfg[3] - evap;
+        }
+      }
+      /* evaporate small precipitation amounts, :2144-2158 */
+      if (qxfg[2] < c.rlmin) { qa[2][4] = qa[2][4] + qxfg[2]; qa[4][2] = qa[4][2] - qxfg[2]; }
+      if (qxfg[3] < c.rlmin) { qa[3][4] = qa[3][4] + qxfg[3]; qa[4][3] = qa[4][3] - qxfg[3]; }
+
+      /* ================= 5.1 solver for cloud cover, :2168-2180 =========================== */
+      T anew = (a + solac) / (one + solab);
+      anew = mn(anew, one);
+      if (anew < c.ramin) anew = zero;
+      const T da = anew - aorig;
+      s.anewm1 = anew;
+
+      /* ================= 5.2 sink limiter, :2233-2286 ===================================== */
+      /* (the first pass :2207-2227 is overwritten before use) */
+      const T qx5[5] = {qx[0], qx[1], qx[2], qx[3], qv};
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        T psum = zero;
+#pragma unroll
+        for (int n = 0; n < 5; ++n) psum = psum + qa[n][m];
+        const T sinksum = zero - psum;
+        const T mm = mx(qx5[m], zepsec);
+        const T rr = mx(sinksum, mm);
+        const T ratio = mm / rr;
+#pragma unroll
+        for (int n = 0; n < 5; ++n) {
+          if (qa[n][m] < zero) {
+            qa[n][m] = qa[n][m] * ratio;
+            qa[m][n] = qa[m][n] * ratio;
+          }
+        }
+      }
+
+      /* ================= 5.2.2 implicit solve, :2294-2397 ================================= */
+      /*
+       * RHS :2326-2337.  LHS: diag d_m = 1 + fallsink_m + sum_n qb[m][n], off-diagonals -qb[m][n];
+       * the only non-zero qb are (l,l) (i,i) (l,s) (i,s), i.e. the transposed system is lower
+       * triangular with the single sub-diagonal row "snow <- liquid, ice".  The reference's
+       * non-pivoting LU then produces exactly two multipliers, -qb03/d0 and -qb13/d1, leaves
+       * every diagonal unchanged, and the back-substitution is a plain divide per species.
+       */
+      T qxn[5];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        T expl = zero;
+#pragma unroll
+        for (int n = 0; n < 5; ++n) expl = expl + qa[n][m];
+        qxn[m] = qx5[m] + expl;
+      }
+      {
+        const T d0 = ((one + zero) + qb00) + qb03;
+        const T d1 = ((one + fallsink1) + qb11) + qb13;
+        const T d2 = one + fallsink2;
+        const T d3 = one + fallsink3;
+        const T l03 = (-qb03) / d0;
+        const T l13 = (-qb13) / d1;
+        qxn[3] = qxn[3] - l03 * qxn[0];
+        qxn[3] = qxn[3] - l13 * qxn[1];
+        qxn[3] = qxn[3] / d3;
+        qxn[2] = qxn[2] / d2;
+        qxn[1] = qxn[1] / d1;
+        qxn[0] = qxn[0] / d0;
+      }
+      /* clip small/negative values into vapour, :2402-2412 */
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        if (qxn[n] < zepsec) { qxn[4] = qxn[4] + qxn[n]; qxn[n] = zero; }
+      }
+      /* variables needed for next level, :2417-2423 */
+      s.qlnm1 = qxn[0]; s.qinm1 = qxn[1];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) qxn2d[m] = qxn[m];
+
+      /* 5.3 precipitation/sedimentation fluxes to next level, :2430-2448 */
+      pf_i_n = (fallsink1 * qxn[1]) * rdtgdp;
+      pf_r_n = (fallsink2 * qxn[2]) * rdtgdp;
+      pf_s_n = (fallsink3 * qxn[3]) * rdtgdp;
+      if (pf_s_n + pf_r_n < zepsec) s.covptot = zero;
+
+      /* ================= 6. tendencies, :2456-2506 ======================================== */
+      {
+        T fluxq = (psupsrce0 + convsrce0) - (zero + convsink) * qxn[0];
+        tend_t = tend_t + (c.ralvdcp * (qxn[0] - qx[0] - fluxq)) * zqtmst;
+        fluxq = ((psupsrce1 + convsrce1) + fallsrce1) - (fallsink1 + convsink) * qxn[1];
+        tend_t = tend_t + (c.ralsdcp * (qxn[1] - qx[1] - fluxq)) * zqtmst;
+        fluxq = fallsrce2 - fallsink2 * qxn[2];
+        tend_t = tend_t + (c.ralvdcp * (qxn[2] - qx[2] - fluxq)) * zqtmst;
+        fluxq = fallsrce3 - fallsink3 * qxn[3];
+        tend_t = tend_t + (c.ralsdcp * (qxn[3] - qx[3] - fluxq)) * zqtmst;
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) tcld[m] = (qxn[m] - qx0[m]) * zqtmst;
+      tend_q = tend_q + (qxn[4] - qv) * zqtmst;
+      tend_a = da * zqtmst;
+      covptot_out = s.covptot;
+    } /* k >= ktop */
+
+    /* ---- write the level's tendencies (single store per element) */
+    io.template st<OUT_TT>(k, tend_t);
+    io.template st<OUT_TQ>(k, tend_q);
+    io.template st<OUT_TA>(k, tend_a);
+    io.template st<OUT_TCLD0>(k, tcld[0]); io.template st<OUT_TCLD1>(k, tcld[1]);
+    io.template st<OUT_TCLD2>(k, tcld[2]); io.template st<OUT_TCLD3>(k, tcld[3]);
+    io.template st<OUT_TCLD4>(k, zero);    /* cloudsc_driver.c:200 */
+    io.template st<OUT_COVPTOT>(k, covptot_out); /* :2505; zero above ncldtop per cloudsc_driver.c:199 */
+
+    /* ================= 8. flux diagnostics for row k+1, :2521-2582 ========================= */
+    {
+      const T pfplsl = pf_r_n + zero;     /* zpfplsx[r] + zpfplsx[l] */
+      const T pfplsn = pf_s_n + pf_i_n;   /* zpfplsx[s] + zpfplsx[i] */
+      io.template st<OUT_FPLSL>(k + 1, pfplsl);
+      io.template st<OUT_FPLSN>(k + 1, pfplsn);
+      io.template st<OUT_FHPSL>(k + 1, -c.rlvtt * pfplsl);
+      io.template st<OUT_FHPSN>(k + 1, -c.rlstt * pfplsn);
+
+      const T gdph_r = (-zrg_r * (paph_n - s.paph_k)) * zqtmst;
+      const T pvfl = io.template ld<IN_PVFL>(k), pvfi = io.template ld<IN_PVFI>(k);
+      /* rain/snow rows copy the liquid/ice running sums of the level above (:2550-2555) */
+      const T fsqrf = s.fsqlf + (qxn2d[2] - qx0[2]) * gdph_r;
+      const T fcqrng = s.fcqlng + lneg[2] * gdph_r;
+      const T fsqsf = s.fsqif + (qxn2d[3] - qx0[3]) * gdph_r;
+      const T fcqsng = s.fcqnng + lneg[3] * gdph_r;
+      s.fsqlf = s.fsqlf + (qxn2d[0] - qx0[0] + pvfl * ptsphy - alfa_w * plude_out) * gdph_r;
+      s.fcqlng = s.fcqlng + lneg[0] * gdph_r;
+      s.fsqltur = s.fsqltur + (pvfl * ptsphy) * gdph_r;
+      s.fsqif = s.fsqif + (qxn2d[1] - qx0[1] + pvfi * ptsphy - (one - alfa_w) * plude_out) * gdph_r;
+      s.fcqnng = s.fcqnng + lneg[1] * gdph_r;
+      s.fsqitur = s.fsqitur + (pvfi * ptsphy) * gdph_r;
+      io.template st<OUT_FSQLF>(k + 1, s.fsqlf);   io.template st<OUT_FSQIF>(k + 1, s.fsqif);
+      io.template st<OUT_FSQRF>(k + 1, fsqrf);     io.template st<OUT_FSQSF>(k + 1, fsqsf);
+      io.template st<OUT_FCQLNG>(k + 1, s.fcqlng); io.template st<OUT_FCQNNG>(k + 1, s.fcqnng);
+      io.template st<OUT_FCQRNG>(k + 1, fcqrng);   io.template st<OUT_FCQSNG>(k + 1, fcqsng);
+      io.template st<OUT_FSQLTUR>(k + 1, s.fsqltur); io.template st<OUT_FSQITUR>(k + 1, s.fsqitur);
+    }
+
+    /* ---- shift the level-(k-1) cache */
+    s.tp1_m1 = t; s.a_m1 = a; s.pap_m1 = pap; s.paph_k = paph_n; s.mf_k = mf_n;
+    s.pf_i = pf_i_n; s.pf_r = pf_r_n; s.pf_s = pf_s_n;
+  }
+  io.st_rainfrac(s.rainfrac);
+}
+
+} /* namespace cloudsc */
+#endif

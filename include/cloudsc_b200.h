@@ -1,0 +1,160 @@
+/*
+ * cloudsc_b200.h -- C ABI of the B200-native CLOUDSC hot path (libcloudsc_b200.so).
+ *
+ * Plain C: pointers, ints and doubles only; no CUDA or torch types cross this boundary
+ * (a stream is passed as an opaque `void*` = cudaStream_t, NULL = default stream).
+ * Every entry point returns 0 on success and a non-zero code otherwise
+ * (CLOUDSC_B200_E* below, or a cudaError_t value); nothing here ever calls exit().
+ * `cloudsc_b200_last_error()` returns a human-readable description of the last failure
+ * on the calling thread.
+ *
+ * What each entry point replaces in the reference (paths relative to the dwarf-p-cloudsc
+ * checkout, src/cloudsc_c/cloudsc/...):
+ *
+ *   cloudsc_c()                      cloudsc_c.h:18-29 / cloudsc_c.c:19-2587   binary-compatible
+ *                                    drop-in: same 61 arguments, host pointers, one NPROMA block,
+ *                                    reads the yrecldp/yomcst/yoethf globals, returns 0.
+ *   cloudsc_b200_set_params()        the implicit global inputs of cloudsc_c() (cloudsc_c.c:385-391,
+ *                                    every yrecldp-> / rg / r2es ... use) snapshotted into
+ *                                    __constant__ memory.
+ *   cloudsc_b200_launch()            the OpenMP block loop of cloudsc_driver.c:183-229, incl. the
+ *                                    zeroing of pcovptot / tendency_loc_cld at :199-200, as ONE
+ *                                    kernel launch over a contiguous range of NPROMA blocks of
+ *                                    device-resident fields.
+ *   cloudsc_b200_run_host()          the same loop for HOST-resident fields: chunked, pinned,
+ *                                    multi-stream H2D || kernel || D2H pipeline (successor of
+ *                                    src/cloudsc_cuda/cloudsc/cloudsc_driver.cu:346-447).
+ *   cloudsc_b200_create()/upload()/  the cudaMalloc / cudaMemcpy block of
+ *     download()/destroy()           src/cloudsc_cuda/cloudsc/cloudsc_driver.cu:276-447.
+ *
+ * Field tables: all bulk entry points take the 56 field pointers of cloudsc_c() as ONE array
+ * `void *fields[CLOUDSC_NFIELDS]`, indexed by `enum cloudsc_field` = position in the
+ * cloudsc_c() argument list.  Global layout per field is the driver's:
+ * [nblocks][shape-of-one-block], NPROMA fastest (cloudsc_driver.c:193-196).
+ */
+#ifndef CLOUDSC_B200_H
+#define CLOUDSC_B200_H
+
+#include <stddef.h>
+#include "cloudsc_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* kind:  L = [klev][nproma], H = [klev+1][nproma], C = [nclv][klev][nproma], S = [nproma] double,
+ *        I = [nproma] int
+ * use:   R read, W written, B both (in/out), N never touched by the kernel,
+ *        A read only when the matching yrecldp->laer* flag is set (unsupported -> EPARAMS) */
+#define CLOUDSC_FIELDS(X) \
+  X(PT, L, R) X(PQ, L, R) \
+  X(TENDENCY_CML_T, L, N) X(TENDENCY_CML_Q, L, N) X(TENDENCY_CML_A, L, N) X(TENDENCY_CML_CLD, C, N) \
+  X(TENDENCY_TMP_T, L, R) X(TENDENCY_TMP_Q, L, R) X(TENDENCY_TMP_A, L, R) X(TENDENCY_TMP_CLD, C, R) \
+  X(TENDENCY_LOC_T, L, W) X(TENDENCY_LOC_Q, L, W) X(TENDENCY_LOC_A, L, W) X(TENDENCY_LOC_CLD, C, W) \
+  X(PVFA, L, N) X(PVFL, L, R) X(PVFI, L, R) X(PDYNA, L, N) X(PDYNL, L, N) X(PDYNI, L, N) \
+  X(PHRSW, L, R) X(PHRLW, L, R) X(PVERVEL, L, R) X(PAP, L, R) X(PAPH, H, R) X(PLSM, S, R) \
+  X(KTYPE, I, R) X(PLU, L, R) X(PLUDE, L, B) X(PSNDE, L, R) X(PMFU, L, R) X(PMFD, L, R) \
+  X(PA, L, R) X(PCLV, C, R) X(PSUPSAT, L, R) \
+  X(PLCRIT_AER, L, A) X(PICRIT_AER, L, A) X(PRE_ICE, L, A) X(PCCN, L, A) X(PNICE, L, A) \
+  X(PCOVPTOT, L, W) X(PRAINFRAC_TOPRFZ, S, W) \
+  X(PFSQLF, H, W) X(PFSQIF, H, W) X(PFCQNNG, H, W) X(PFCQLNG, H, W) X(PFSQRF, H, W) \
+  X(PFSQSF, H, W) X(PFCQRNG, H, W) X(PFCQSNG, H, W) X(PFSQLTUR, H, W) X(PFSQITUR, H, W) \
+  X(PFPLSL, H, W) X(PFPLSN, H, W) X(PFHPSL, H, W) X(PFHPSN, H, W)
+
+enum cloudsc_field {
+#define CLOUDSC_X(name, kind, use) CLOUDSC_F_##name,
+  CLOUDSC_FIELDS(CLOUDSC_X)
+#undef CLOUDSC_X
+  CLOUDSC_NFIELDS /* = 56 */
+};
+
+enum {
+  CLOUDSC_B200_OK = 0,
+  CLOUDSC_B200_EPARAMS = -1,   /* parameter set outside what the kernel is specialised for */
+  CLOUDSC_B200_EARG = -2,      /* bad argument (NULL field, klev/nproma/ngptot out of range) */
+  CLOUDSC_B200_ENOTINIT = -3,  /* set_params() has not been called on this device */
+  CLOUDSC_B200_ENOMEM = -4
+};
+
+/* Precision of the device arithmetic / device field storage. */
+enum { CLOUDSC_B200_FP64 = 0, CLOUDSC_B200_FP32 = 1 };
+
+/* ---- information ------------------------------------------------------------------------ */
+const char *cloudsc_b200_version(void);
+const char *cloudsc_b200_last_error(void);
+/* number of visible CUDA devices, or a negative CLOUDSC_B200_E* / -cudaError code */
+int cloudsc_b200_device_count(void);
+/* name/kind/use of field `f` as one-letter codes from the table above (for bindings) */
+const char *cloudsc_b200_field_name(int f);
+char cloudsc_b200_field_kind(int f);
+char cloudsc_b200_field_use(int f);
+/* elements one NPROMA block of field f holds (e.g. klev*nproma) */
+size_t cloudsc_b200_field_block_elems(int f, int nproma, int klev);
+
+/* ---- parameters -> __constant__ memory of the current device ---------------------------- */
+int cloudsc_b200_set_params(const struct TECLDP *ydecldp, const struct cloudsc_consts *consts);
+/* convenience for C callers that use the reference's globals (yrecldp, rg, r2es, ...) */
+int cloudsc_b200_set_params_from_globals(void);
+
+/* ---- device-resident launch ------------------------------------------------------------- */
+/*
+ * Run CLOUDSC on columns [0, ngptot) held in device memory as `nblocks = ceil(ngptot/nproma)`
+ * blocks.  `dev_fields[f]` are device pointers (may be NULL for use N / A fields).
+ * precision = CLOUDSC_B200_FP64: fields are double; FP32: fields are float (KTYPE stays int).
+ * Asynchronous on `stream`.  PLUDE is in/out (cloudsc_c.c:970,980).
+ */
+int cloudsc_b200_launch(void *const dev_fields[CLOUDSC_NFIELDS], int ngptot, int nproma, int klev,
+                        double ptsphy, int precision, void *stream);
+
+/* Kernel variant selection for sweeps/profiling: 0 = default (auto). See DESIGN.md. */
+int cloudsc_b200_set_variant(int variant);
+int cloudsc_b200_get_variant(void);
+/* registers/thread, spill bytes, static smem, max threads/block, achieved blocks/SM of the
+ * kernel the next launch(nproma, precision) would use; out[8] ints */
+int cloudsc_b200_kernel_info(int nproma, int precision, int out[8]);
+
+/* ---- host-resident, end-to-end ---------------------------------------------------------- */
+/*
+ * Same computation with HOST pointers (pageable or pinned), all blocks: stages chunks of
+ * `chunk_blocks` NPROMA-blocks through pinned buffers on `nstreams` streams (0 = defaults),
+ * uploading only fields with use R/B and downloading only W/B.  Synchronous.
+ * If `stats` != NULL it receives {h2d_bytes, d2h_bytes, kernel_ms_sum, wall_ms}.
+ */
+int cloudsc_b200_run_host(void *const host_fields[CLOUDSC_NFIELDS], int ngptot, int nproma, int klev,
+                          double ptsphy, int chunk_blocks, int nstreams, double stats[4]);
+
+/* ---- handle API: resident device state for a fixed geometry (one handle per GPU) --------- */
+typedef struct cloudsc_b200_state cloudsc_b200_state;
+int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc_b200_state **out);
+int cloudsc_b200_destroy(cloudsc_b200_state *st);
+/* H2D of every R/B field (host doubles; converted on the fly for FP32 states) */
+int cloudsc_b200_upload(cloudsc_b200_state *st, void *const host_fields[CLOUDSC_NFIELDS], void *stream);
+/* D2H of every W/B field */
+int cloudsc_b200_download(cloudsc_b200_state *st, void *const host_fields[CLOUDSC_NFIELDS], void *stream);
+/* launch over blocks [first_block, first_block+nblocks) of the state; nblocks<=0 -> all */
+int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, int nblocks, void *stream);
+/* restore PLUDE from the pristine copy kept at upload() (the kernel scales it in place) */
+int cloudsc_b200_reset_inout(cloudsc_b200_state *st, void *stream);
+/* device pointer of field f inside the state (for zero-copy consumers) */
+void *cloudsc_b200_field_ptr(cloudsc_b200_state *st, int f);
+int cloudsc_b200_sync(void *stream);
+
+/* ---- binary-compatible drop-in for the reference kernel (host pointers, one block) -------- */
+int cloudsc_c(int kidia, int kfdia, int klon, int klev, double ptsphy,
+  double *v_pt, double *v_pq,
+  double *v_tendency_cml_t, double *v_tendency_cml_q, double *v_tendency_cml_a, double *v_tendency_cml_cld,
+  double *v_tendency_tmp_t, double *v_tendency_tmp_q, double *v_tendency_tmp_a, double *v_tendency_tmp_cld,
+  double *v_tendency_loc_t, double *v_tendency_loc_q, double *v_tendency_loc_a, double *v_tendency_loc_cld,
+  double *v_pvfa, double *v_pvfl, double *v_pvfi, double *v_pdyna, double *v_pdynl, double *v_pdyni,
+  double *v_phrsw, double *v_phrlw, double *v_pvervel, double *v_pap, double *v_paph, double *v_plsm,
+  int *v_ktype, double *v_plu, double *v_plude, double *v_psnde, double *v_pmfu, double *v_pmfd,
+  double *v_pa, double *v_pclv, double *v_psupsat, double *v_plcrit_aer, double *v_picrit_aer,
+  double *v_pre_ice, double *v_pccn, double *v_pnice, double *v_pcovptot, double *v_prainfrac_toprfz,
+  double *v_pfsqlf, double *v_pfsqif, double *v_pfcqnng, double *v_pfcqlng, double *v_pfsqrf,
+  double *v_pfsqsf, double *v_pfcqrng, double *v_pfcqsng, double *v_pfsqltur, double *v_pfsqitur,
+  double *v_pfplsl, double *v_pfplsn, double *v_pfhpsl, double *v_pfhpsn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOUDSC_B200_H */

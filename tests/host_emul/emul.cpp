@@ -1,0 +1,102 @@
+/*
+ * emul.cpp -- TEST-ONLY host build of the device column code (csrc/cloudsc_column.cuh).
+ *
+ * Compiles the exact header the CUDA kernels instantiate, for the host, with FP contraction off,
+ * so that `-m "not gpu"` tests can check the re-organised (k-cached, sparse-solve) arithmetic
+ * bit-for-bit against the reference kernel without a GPU.  Never linked into, loaded by, or
+ * reachable from the product library: libcloudsc_b200.so has no host arithmetic path.
+ */
+#include <cstddef>
+#include <cstring>
+#include "cloudsc_b200.h"
+#include "cloudsc_column.cuh"
+#include "cloudsc_fill.h"
+
+namespace {
+using namespace cloudsc;
+
+template <typename T>
+struct HostIO {
+  void *const *f;  /* block-offset field table */
+  int jl, stride, klev;
+  static int in_field(int s) {
+    static const int m[N_IN] = {CLOUDSC_F_PT, CLOUDSC_F_PQ, CLOUDSC_F_TENDENCY_TMP_T, CLOUDSC_F_TENDENCY_TMP_Q,
+      CLOUDSC_F_TENDENCY_TMP_A, CLOUDSC_F_PA, CLOUDSC_F_PAP, CLOUDSC_F_PSUPSAT, CLOUDSC_F_PLUDE, CLOUDSC_F_PLU,
+      CLOUDSC_F_PSNDE, CLOUDSC_F_PMFU, CLOUDSC_F_PMFD, CLOUDSC_F_PHRSW, CLOUDSC_F_PHRLW, CLOUDSC_F_PVERVEL,
+      CLOUDSC_F_PVFL, CLOUDSC_F_PVFI, CLOUDSC_F_PCLV, CLOUDSC_F_PCLV, CLOUDSC_F_PCLV, CLOUDSC_F_PCLV,
+      CLOUDSC_F_TENDENCY_TMP_CLD, CLOUDSC_F_TENDENCY_TMP_CLD, CLOUDSC_F_TENDENCY_TMP_CLD, CLOUDSC_F_TENDENCY_TMP_CLD,
+      CLOUDSC_F_PAPH};
+    return m[s];
+  }
+  static int out_field(int s) {
+    static const int m[N_OUT] = {CLOUDSC_F_TENDENCY_LOC_T, CLOUDSC_F_TENDENCY_LOC_Q, CLOUDSC_F_TENDENCY_LOC_A,
+      CLOUDSC_F_TENDENCY_LOC_CLD, CLOUDSC_F_TENDENCY_LOC_CLD, CLOUDSC_F_TENDENCY_LOC_CLD, CLOUDSC_F_TENDENCY_LOC_CLD,
+      CLOUDSC_F_TENDENCY_LOC_CLD, CLOUDSC_F_PCOVPTOT, CLOUDSC_F_PLUDE,
+      CLOUDSC_F_PFSQLF, CLOUDSC_F_PFSQIF, CLOUDSC_F_PFCQNNG, CLOUDSC_F_PFCQLNG, CLOUDSC_F_PFSQRF, CLOUDSC_F_PFSQSF,
+      CLOUDSC_F_PFCQRNG, CLOUDSC_F_PFCQSNG, CLOUDSC_F_PFSQLTUR, CLOUDSC_F_PFSQITUR, CLOUDSC_F_PFPLSL,
+      CLOUDSC_F_PFPLSN, CLOUDSC_F_PFHPSL, CLOUDSC_F_PFHPSN};
+    return m[s];
+  }
+  template <int S> T ld(int k) const {
+    const int sp = (S >= IN_PCLV0 && S <= IN_PCLV3) ? S - IN_PCLV0 : (S >= IN_TCLD0 && S <= IN_TCLD3) ? S - IN_TCLD0 : 0;
+    return ((const T *)f[in_field(S)])[(size_t)(sp * klev + k) * stride + jl];
+  }
+  template <int S> void st(int k, T v) {
+    const int sp = (S >= OUT_TCLD0 && S <= OUT_TCLD4) ? S - OUT_TCLD0 : 0;
+    ((T *)f[out_field(S)])[(size_t)(sp * klev + k) * stride + jl] = v;
+  }
+  T plsm() const { return ((const T *)f[CLOUDSC_F_PLSM])[jl]; }
+  int ktype() const { return ((const int *)f[CLOUDSC_F_KTYPE])[jl]; }
+  void st_rainfrac(T v) { ((T *)f[CLOUDSC_F_PRAINFRAC_TOPRFZ])[jl] = v; }
+};
+
+template <typename T>
+int run(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
+        int ngptot, int nproma, int klev, double ptsphy) {
+  if (check_params(p)) return CLOUDSC_B200_EPARAMS;
+  CloudscConst<T> c;
+  fill_consts<T>(p, k, &c);
+  const int nblocks = (ngptot + nproma - 1) / nproma;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < nblocks; b++) {
+    void *pb[CLOUDSC_NFIELDS];
+    for (int f = 0; f < CLOUDSC_NFIELDS; f++) {
+      const size_t off = (size_t)b * cloudsc_b200_field_block_elems(f, nproma, klev);
+      const size_t es = cloudsc_b200_field_kind(f) == 'I' ? sizeof(int) : sizeof(T);
+      pb[f] = fields[f] ? (void *)((char *)fields[f] + off * es) : nullptr;
+    }
+    const int bsize = (ngptot - b * nproma) < nproma ? (ngptot - b * nproma) : nproma;
+    for (int jl = 0; jl < bsize; jl++) {
+      HostIO<T> io{pb, jl, nproma, klev};
+      cloudsc_column<T>(c, io, klev, (T)ptsphy);
+    }
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+/* local copies of the two table helpers so this test library has no dependency on the product .so */
+static const char k_kinds[] = {
+#define CLOUDSC_X(name, kind, use) #kind[0],
+  CLOUDSC_FIELDS(CLOUDSC_X)
+#undef CLOUDSC_X
+  0};
+char cloudsc_b200_field_kind(int f) { return k_kinds[f]; }
+size_t cloudsc_b200_field_block_elems(int f, int nproma, int klev) {
+  switch (k_kinds[f]) {
+    case 'L': return (size_t)klev * nproma;
+    case 'H': return (size_t)(klev + 1) * nproma;
+    case 'C': return (size_t)5 * klev * nproma;
+    default: return (size_t)nproma;
+  }
+}
+int cloudsc_emul_blocks_f64(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
+                            int ngptot, int nproma, int klev, double ptsphy) {
+  return run<double>(p, k, fields, ngptot, nproma, klev, ptsphy);
+}
+int cloudsc_emul_blocks_f32(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
+                            int ngptot, int nproma, int klev, double ptsphy) {
+  return run<float>(p, k, fields, ngptot, nproma, klev, ptsphy);
+}
+}

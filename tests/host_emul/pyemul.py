@@ -1,0 +1,29 @@
+"""ctypes front-end of tests/host_emul/libcloudsc_emul.so (test-only host build of the device column code)."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Emul:
+    def __init__(self):
+        self.lib = ctypes.CDLL(os.path.join(HERE, "libcloudsc_emul.so"), mode=ctypes.RTLD_LOCAL)
+        for n in ("cloudsc_emul_blocks_f64", "cloudsc_emul_blocks_f32"):
+            fn = getattr(self.lib, n)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                           ctypes.c_int, ctypes.c_int, ctypes.c_double]
+
+    def run(self, fields, p, k, ngptot, nproma, klev, ptsphy, dtype=np.float64):
+        from dwarf_p_cloudsc_b200.params import FIELDS
+        tab = (ctypes.c_void_p * len(FIELDS))()
+        for f in FIELDS:
+            a = fields[f.name]
+            assert a.flags["C_CONTIGUOUS"] and a.dtype == (np.int32 if f.kind == "I" else dtype), f.name
+            tab[f.index] = a.ctypes.data
+        fn = self.lib.cloudsc_emul_blocks_f64 if dtype == np.float64 else self.lib.cloudsc_emul_blocks_f32
+        rc = fn(ctypes.addressof(p), ctypes.addressof(k), tab, ngptot, nproma, klev, ptsphy)
+        if rc:
+            raise RuntimeError(f"emulation returned {rc}")
