@@ -1,0 +1,40 @@
+/*
+ * cloudsc_kernels.cuh -- launch interface between the C ABI (cloudsc_abi.cu) and the sm_100a
+ * kernels (cloudsc_kernels.cu).  Internal; not part of the public ABI.
+ */
+#ifndef CLOUDSC_KERNELS_CUH
+#define CLOUDSC_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include "cloudsc_b200.h"
+#include "cloudsc_consts.h"
+
+namespace cloudsc {
+
+/* the 56 field pointers of cloudsc_c(), passed to the kernel by value (448 B of param space) */
+struct FieldTable {
+  void *p[CLOUDSC_NFIELDS];
+};
+
+/* geometry of one launch: columns [col_begin, col_end) of a field set blocked by nproma */
+struct LaunchGeom {
+  int col_begin;  /* first global column (0-based) */
+  int col_end;    /* one past the last global column */
+  int nproma;
+  int klev;
+};
+
+enum Variant {
+  VARIANT_AUTO = 0,
+  VARIANT_DIRECT = 1,   /* one thread per column, loads/stores straight from/to global memory */
+  VARIANT_STAGED = 2,   /* warp-private TMA (cp.async.bulk) + mbarrier staging of the level tiles */
+  VARIANT_COUNT
+};
+
+cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<float> &c32);
+cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,
+                         cudaStream_t stream);
+cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]);
+
+}  // namespace cloudsc
+#endif

@@ -69,11 +69,14 @@ def expand(src: np.ndarray, ngptot: int, nproma: int, first_column: int = 0) -> 
 
 
 def blocked_fields(cols: Dict[str, np.ndarray], ngptot: int, nproma: int, klev: int,
-                   first_column: int = 0, dtype=np.float64) -> Dict[str, np.ndarray]:
-    """All 56 fields in driver layout: inputs expanded, everything else zero-initialised."""
+                   first_column: int = 0, dtype=np.float64, live_only: bool = True) -> Dict[str, np.ndarray]:
+    """Fields in driver layout: inputs expanded, outputs zero-initialised.  With ``live_only`` the
+    13 fields the kernel never touches (use N / A in the field table) are left out (NULL pointers)."""
     nb = nblocks_of(ngptot, nproma)
     out = {}
     for f in FIELDS:
+        if live_only and f.use in "NA":
+            continue
         shape = (nb,) + f.level_shape(klev) + (nproma,)
         if f.name in cols:
             a = expand(cols[f.name], ngptot, nproma, first_column)

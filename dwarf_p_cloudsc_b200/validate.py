@@ -1,0 +1,95 @@
+"""The dwarf's error table (``cloudsc_validate``) with an explicit pass/fail bar.
+
+Semantics follow src/cloudsc_c/cloudsc/cloudsc_validate.c:20-115 per field over the VALID columns:
+min, max, AbsMaxErr = max|f-ref|, AvgAbsErr/GP = sum|f-ref| / ngptot, and the "MaxRelErr-%" column
+    0                       if sum|f-ref| < eps
+    sum|err| / (1 + zsum)   if zsum < eps
+    sum|err| / zsum         otherwise                     (x100; " !!!!" if > 10 eps)
+where the reference accumulates ``zsum += abs(ref)`` with the *integer* ``abs`` (cloudsc_validate.c:74,109,147;
+SURVEY App. C.1), i.e. every |ref| < 1 counts as 0.  We print that reference-compatible number AND the
+true relative L1 error, and judge on the latter:
+
+    FP64 bar:   sum|err|/sum|ref| <= 1e-10   and   AbsMaxErr <= 1e-9 * max|ref|
+    FP32 bar (proposed, no reference):  sum|err|/sum|ref| <= 1e-3    (AbsMaxErr reported only)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, NamedTuple
+
+import numpy as np
+
+from .state import VALIDATE_ORDER, unblock
+
+EPS = float(np.finfo(np.float64).eps)
+FP64_L1_TOL = 1.0e-10
+FP64_MAX_TOL = 1.0e-9
+FP32_L1_TOL = 1.0e-3
+
+_PRINT_NAME = {"TENDENCY_LOC_A": "TENDENCY_LOC%A", "TENDENCY_LOC_Q": "TENDENCY_LOC%Q",
+               "TENDENCY_LOC_T": "TENDENCY_LOC%T", "TENDENCY_LOC_CLD": "TENDENCY_LOC%CLD"}
+
+
+class FieldError(NamedTuple):
+    name: str
+    minval: float
+    maxval: float
+    maxerr: float
+    errsum: float
+    refsum_true: float      # sum |ref|
+    refsum_c: float         # sum (int)|ref|, the C validator's zsum
+    refmax: float
+    avgpgp: float
+    relerr_c: float         # the reference's "MaxRelErr-%" (already x100)
+    iopt: int
+    rel_l1: float           # true sum|err|/sum|ref|
+    flagged: bool           # the reference's " !!!!"
+
+    def passes(self, precision: str = "fp64") -> bool:
+        if not np.isfinite([self.maxerr, self.errsum, self.minval, self.maxval]).all():
+            return False
+        if precision == "fp32":
+            return self.rel_l1 <= FP32_L1_TOL
+        return self.rel_l1 <= FP64_L1_TOL and self.maxerr <= FP64_MAX_TOL * max(self.refmax, 1e-300)
+
+
+def field_error(name: str, got: np.ndarray, ref: np.ndarray, ngptot: int) -> FieldError:
+    """got/ref: arrays over valid columns only, any shape (same for both)."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    diff = np.abs(got - ref)
+    errsum = float(diff.sum())
+    refsum_true = float(np.abs(ref).sum())
+    refsum_c = float(np.trunc(np.abs(ref)).sum())     # int abs() on a double truncates toward zero
+    if errsum < EPS:
+        rel, iopt = 0.0, 1
+    elif refsum_c < EPS:
+        rel, iopt = errsum / (1.0 + refsum_c), 2
+    else:
+        rel, iopt = errsum / refsum_c, 3
+    rel_l1 = 0.0 if errsum == 0.0 else (errsum / refsum_true if refsum_true > 0 else float("inf"))
+    return FieldError(name, float(got.min()), float(got.max()), float(diff.max()), errsum, refsum_true, refsum_c,
+                      float(np.abs(ref).max()), errsum / ngptot, 100.0 * rel, iopt, rel_l1, rel > 10.0 * EPS)
+
+
+def validate(fields: Dict[str, np.ndarray], reference: Dict[str, np.ndarray], ngptot: int) -> List[FieldError]:
+    """fields/reference: blocked arrays [nb, ..., nproma] of the 21 validated outputs."""
+    out = []
+    for name in VALIDATE_ORDER:
+        out.append(field_error(name, unblock(np.asarray(fields[name]), ngptot),
+                               unblock(np.asarray(reference[name]), ngptot), ngptot))
+    return out
+
+
+def format_table(errs: List[FieldError], precision: str = "fp64") -> str:
+    """The reference's table layout (cloudsc_validate.c:44,193) plus two columns of ours."""
+    lines = [" %20s %s %20s %20s %20s %20s %20s   %12s %s" % (
+        "Variable", "Dim", "MinValue", "MaxValue", "AbsMaxErr", "AvgAbsErr/GP", "MaxRelErr-%", "L1rel(true)", "ok")]
+    for e in errs:
+        lines.append(" %20s %dD%d %20.13e %20.13e %20.13e %20.13e %20.13e %s %12.5e %s" % (
+            _PRINT_NAME.get(e.name, e.name), 2, e.iopt, e.minval, e.maxval, e.maxerr, e.avgpgp, e.relerr_c,
+            " !!!!" if e.flagged else "     ", e.rel_l1, "PASS" if e.passes(precision) else "FAIL"))
+    return "\n".join(lines)
+
+
+def all_pass(errs: List[FieldError], precision: str = "fp64") -> bool:
+    return all(e.passes(precision) for e in errs)

@@ -56,7 +56,9 @@ class _Oracle:
         self.set_params(p, k)
         tab = (ctypes.c_void_p * len(FIELDS))()
         for f in FIELDS:
-            a = fields[f.name]
+            a = fields.get(f.name)
+            if a is None:
+                continue
             assert a.flags["C_CONTIGUOUS"] and a.dtype == (np.int32 if f.kind == "I" else np.float64), f.name
             tab[f.index] = a.ctypes.data
         t = self.fn(int(nthreads), int(ngptot), int(nproma), int(klev), float(ptsphy), tab)

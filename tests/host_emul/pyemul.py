@@ -20,7 +20,9 @@ class Emul:
         from dwarf_p_cloudsc_b200.params import FIELDS
         tab = (ctypes.c_void_p * len(FIELDS))()
         for f in FIELDS:
-            a = fields[f.name]
+            a = fields.get(f.name)
+            if a is None:
+                continue
             assert a.flags["C_CONTIGUOUS"] and a.dtype == (np.int32 if f.kind == "I" else dtype), f.name
             tab[f.index] = a.ctypes.data
         fn = self.lib.cloudsc_emul_blocks_f64 if dtype == np.float64 else self.lib.cloudsc_emul_blocks_f32
