@@ -31,7 +31,7 @@ def _load() -> ctypes.CDLL:
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -m dwarf_p_cloudsc_b200.build` "
             "(there is no CPU fallback for the CLOUDSC hot path)")
-    return ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    return ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
 
 
 lib = _load()

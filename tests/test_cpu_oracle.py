@@ -1,0 +1,151 @@
+"""CPU-side parity chain (`-m "not gpu"`):
+
+    reference.h5 (Fortran kernel)  <-3e-13->  compiled reference C kernel (oracle/_ref, when present)
+         <-bit exact->  C restatement (oracle/cloudsc_oracle.c)
+         <-bit exact->  host build of the DEVICE column code (tests/host_emul, FP contraction off)
+
+so that on the GPU only FMA contraction and the CUDA libm separate the kernel from the reference.
+"""
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VARIANTS = ["", "warm", "hot+land", "conv+land", "rain+warm", "moist+tend",
+            "warm+land+conv+rain+moist+tend", "hot+rain+moist+conv"]
+
+
+def _oracles(built):
+    import pyoracle
+    out = []
+    for cls in (pyoracle.RefOracle, pyoracle.PortOracle):
+        try:
+            out.append(cls())
+        except (FileNotFoundError, OSError):
+            pass
+    assert out, "no CPU oracle could be loaded"
+    return out
+
+
+def test_oracles_reproduce_reference_h5(built, input_data):
+    """Pins the oracle: every CPU checker vs the golden vectors of the reference's own data set.
+    Bars = what the compiled reference kernel itself achieves against the Fortran-generated file
+    (SURVEY App. D): L1-relative <= 1e-15, point-wise relative <= 1e-12 where |ref| > 1e-3 max|ref|."""
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    ref = state.load_reference()
+    for orc in _oracles(built):
+        for nproma in (100, 16):
+            F = state.blocked_fields(cols, 100, nproma, klev)
+            orc.run(F, p, k, 100, nproma, klev, scalars["PTSPHY"], 2)
+            for name in state.VALIDATE_ORDER:
+                got, exp = state.unblock(F[name], 100), ref[name]
+                err = np.abs(got - exp)
+                denom = np.abs(exp).sum()
+                assert err.sum() <= 1e-15 * denom + 1e-300, (orc.kind, name, err.sum() / max(denom, 1e-300))
+                big = np.abs(exp) > 1e-3 * np.abs(exp).max()
+                if big.any():
+                    assert (err[big] / np.abs(exp[big])).max() <= 1e-12, (orc.kind, name)
+
+
+def test_port_is_bit_identical_to_reference_build(built, input_data):
+    import pyoracle
+    try:
+        ref, port = pyoracle.RefOracle(), pyoracle.PortOracle()
+    except (FileNotFoundError, OSError):
+        pytest.skip("needs both oracle/_ref and the port (reference checkout not present)")
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    for variant in VARIANTS:
+        c2 = state.perturb(cols, variant)
+        A = state.blocked_fields(c2, 150, 32, klev)
+        B = {n: a.copy() for n, a in A.items()}
+        ref.run(A, p, k, 150, 32, klev, scalars["PTSPHY"], 1)
+        port.run(B, p, k, 150, 32, klev, scalars["PTSPHY"], 1)
+        for f in params.OUTPUT_FIELDS:
+            a, b = state.unblock(A[f.name], 150), state.unblock(B[f.name], 150)
+            assert np.isfinite(a).all()
+            assert np.array_equal(a, b), (variant, f.name, np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("nssopt", [1, 0, 2, 3])
+def test_device_column_code_host_build_is_bit_identical(built, oracle, input_data, variant, nssopt):
+    """The k-cached / sparse-solve re-organisation is value-identical to the reference algorithm."""
+    if nssopt != 1 and variant not in ("moist+tend", "warm+land+conv+rain+moist+tend"):
+        pytest.skip("nssopt sweep only on the variants that reach 3.4b(2)")
+    import pyemul
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    p.nssopt = nssopt
+    c2 = state.perturb(cols, variant)
+    ngptot, nproma = 100, 16       # 7 blocks, ragged last block (4 valid columns)
+    A = state.blocked_fields(c2, ngptot, nproma, klev)
+    B = {n: a.copy() for n, a in A.items()}
+    oracle.run(A, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+    pyemul.Emul().run(B, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
+    for f in params.OUTPUT_FIELDS:
+        a, b = state.unblock(A[f.name], ngptot), state.unblock(B[f.name], ngptot)
+        assert np.array_equal(a, b), (variant, f.name, float(np.abs(a - b).max()))
+
+
+def test_perturbations_reach_the_cold_branches(built, oracle, input_data):
+    """The synthetic variants must actually exercise what the shipped data leaves cold."""
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    c2 = state.perturb(cols, "warm+land+conv+rain+moist+tend")
+    F = state.blocked_fields(c2, 100, 100, klev)
+    oracle.run(F, p, k, 100, 100, klev, scalars["PTSPHY"], 1)
+    assert c2["PT"].max() > 280.0
+    assert F["PFPLSL"].max() > 0.0                 # rain reaches the ground: melting + warm rain
+    assert np.count_nonzero(F["PRAINFRAC_TOPRFZ"]) > 0   # rain freezing layer found
+    assert F["PFHPSL"].min() < 0.0
+    base = state.blocked_fields(cols, 100, 100, klev)
+    oracle.run(base, p, k, 100, 100, klev, scalars["PTSPHY"], 1)
+    assert base["PFPLSL"].max() == 0.0 and np.count_nonzero(base["PRAINFRAC_TOPRFZ"]) == 0
+
+
+def test_float32_host_build_tracks_float64(built, input_data):
+    """FP32 instantiation of the same column code (config C5).  Single precision moves threshold
+    decisions (rlmin = zepsec = 1e-14 sit below FP32 resolution of the mixing ratios), so the bar here
+    is only "finite and the same climate": measured L1-relative is 5e-6 .. 1.2e-1 per field
+    (DESIGN.md, FP32 section)."""
+    import pyemul
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    A = state.blocked_fields(cols, 100, 100, klev)
+    B = state.blocked_fields(cols, 100, 100, klev, dtype=np.float32)
+    em = pyemul.Emul()
+    em.run(A, p, k, 100, 100, klev, scalars["PTSPHY"])
+    em.run(B, p, k, 100, 100, klev, scalars["PTSPHY"], dtype=np.float32)
+    for name, bar in (("PFPLSN", 2e-2), ("PFHPSN", 2e-2), ("PFSQIF", 1e-1), ("PFSQLF", 3e-1), ("PCOVPTOT", 1e-3),
+                      ("PLUDE", 1e-4), ("TENDENCY_LOC_A", 1e-2)):
+        a, b = A[name], B[name].astype(np.float64)
+        assert np.isfinite(b).all()
+        assert np.abs(a - b).sum() <= bar * np.abs(a).sum(), name
+
+
+def test_oracle_is_not_interposed_by_the_product_library(built, input_data):
+    """libcloudsc_b200.so exports the drop-in symbols cloudsc_c / yrecldp / rg ...; the checkers are
+    linked -Bsymbolic so that they keep using their OWN kernel and parameters even when the product
+    library is loaded first (otherwise parity would compare the GPU path with itself)."""
+    import ctypes
+    import pyoracle
+    from dwarf_p_cloudsc_b200 import api, params, state   # product library loaded BEFORE the oracle
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    ref = state.load_reference()
+    for orc in _oracles(built):
+        own = ctypes.cast(getattr(orc.lib, "cloudsc_c" if orc.kind == "reference" else "cloudsc_oracle"), ctypes.c_void_p).value
+        prod = ctypes.cast(api.lib.cloudsc_c, ctypes.c_void_p).value
+        assert own != prod
+        F = state.blocked_fields(cols, 100, 32, klev)
+        orc.run(F, p, k, 100, 32, klev, scalars["PTSPHY"], 2)
+        got = state.unblock(F["PFPLSN"], 100)
+        assert np.abs(got - ref["PFPLSN"]).max() <= 1e-12 * np.abs(ref["PFPLSN"]).max()
