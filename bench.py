@@ -234,26 +234,27 @@ def run_b200(args, rank, local_rank, world):
 
     # -- end to end through the public host API: pinned host buffers in, host buffers out
     e2e = None
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    plude_host0 = H["PLUDE"].clone()
-    api.run_host(H, ngptot, nproma, klev, pts)            # warm-up (allocations, first touch)
-    if dist:
-        dist.barrier()
-    e2e_ms, h2d, d2h = [], 0, 0
-    for _ in range(e2e_steps):
-        H["PLUDE"].copy_(plude_host0)
-        t0 = time.perf_counter()
-        st = api.run_host(H, ngptot, nproma, klev, pts)
-        e2e_ms.append(1e3 * (time.perf_counter() - t0))
-        h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
-    e2e_t = sum(e2e_ms) / len(e2e_ms)
-    if dist:
-        tt = torch.tensor([e2e_t], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t = float(tt.item())
-    e2e = {"value": world * ngptot / (e2e_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-           "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_t, "steps": e2e_steps,
-           "api": "cloudsc_b200_run_host (C ABI, pinned host fields, chunked multi-stream H2D|kernel|D2H)"}
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        plude_host0 = H["PLUDE"].clone()
+        api.run_host(H, ngptot, nproma, klev, pts)            # warm-up (allocations, first touch)
+        if dist:
+            dist.barrier()
+        e2e_ms, h2d, d2h = [], 0, 0
+        for _ in range(e2e_steps):
+            H["PLUDE"].copy_(plude_host0)
+            t0 = time.perf_counter()
+            st = api.run_host(H, ngptot, nproma, klev, pts)
+            e2e_ms.append(1e3 * (time.perf_counter() - t0))
+            h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
+        e2e_t = sum(e2e_ms) / len(e2e_ms)
+        if dist:
+            tt = torch.tensor([e2e_t], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_t = float(tt.item())
+        e2e = {"value": world * ngptot / (e2e_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_t, "steps": e2e_steps,
+               "api": "cloudsc_b200_run_host (C ABI, pinned host fields, chunked multi-stream H2D|kernel|D2H)"}
 
     if rank != 0:
         if dist:
@@ -311,6 +312,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel sweeps only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

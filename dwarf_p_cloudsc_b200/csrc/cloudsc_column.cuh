@@ -8,23 +8,32 @@
  *    (init :462-513, tidy-up :519-575, saturation :583-640, sweep :732-2508, fluxes :2521-2582,
  *    ~51 KB of stack per column); here every such temporary is a scalar of the current level and
  *    the only state that survives from level k-1 to k is `struct Carry` below.
- *  - the 5x5 source/sink matrices are fully unrolled register arrays; entries that no process ever
- *    writes stay compile-time zeros, and the implicit solve uses the fact that with the shipped
- *    process set (iwarmrain=2) ZSOLQB has only the entries (l,l) (i,i) (l,s) (i,s), so the
- *    non-pivoting LU of :2351-2397 collapses to two multipliers and five divides (derivation at
- *    `solve` below; value-identical to the full elimination, signs of zeros aside).
+ *  - the 5x5 source/sink matrix is a fully unrolled register array; entries no process ever writes
+ *    stay compile-time zeros.  With the shipped process set (iwarmrain=2) ZSOLQB has only the
+ *    entries (l,l) (i,i) (l,s) (i,s), so the non-pivoting LU of :2351-2397 collapses to two
+ *    multipliers and one divide per species (derivation at "5.2.2" below; value-identical to the
+ *    full elimination, signs of zeros aside).  The sink limiter (:2233-2286) only divides when a
+ *    species' sinks really exceed its content (ratio == 1 otherwise, exactly as in the reference).
  *  - every output element is written exactly once (the reference read-modify-writes the
  *    tendencies, :526-567 then :2465-2498, and re-reads the flux sums, :2548-2568).
- *  - parameters come from `CloudscConst<T>` (constant memory on the device).
+ *  - parameters come from `CloudscConst<T>` (__constant__ memory) and `StepConst<T>` (kernel
+ *    parameter bank); no parameter is ever read from global memory.
  *
- * Floating-point evaluation order follows the reference statement by statement (comments give
- * the cloudsc_c.c line), so that a host build of this header with contraction disabled is
- * bit-identical to the reference on the same inputs (tests/host_emul) and the GPU build differs
- * only by FMA contraction and the CUDA libm.
+ * Two arithmetic modes, selected at compile time:
  *
- * The code is generic over the arithmetic type T (double, float) and over an IO policy that
- * provides level-indexed loads/stores (plain global memory, or the TMA-staged shared-memory
- * pipeline in cloudsc_kernels.cu).  Physics switches are specialised on the values the reference
+ *   CLOUDSC_STRICT=1  statement-by-statement evaluation order of the reference (comments give the
+ *                     cloudsc_c.c line).  A host build of this header in this mode with FP
+ *                     contraction off is BIT-IDENTICAL to the reference on the same inputs
+ *                     (tests/host_emul, tests/test_cpu_oracle.py) -- that is the proof that the
+ *                     k-caching / sparse-solve re-organisation preserves the algorithm.
+ *   CLOUDSC_STRICT=0  (the product kernels) same algorithm with shared reciprocals
+ *                     (a/b and c/b -> r=1/b; a*r; c*r), a Newton reciprocal without the IEEE
+ *                     special-case path and a branch-free exp() -- each within ~2 ulp of the strict
+ *                     operation.  tests/ bound the end-to-end effect (CPU: fast-vs-reference;
+ *                     GPU: the dwarf's error table within BASELINE.md's tolerance).
+ *
+ * Generic over the arithmetic type T (double, float) and over an IO policy providing
+ * level-indexed loads/stores.  Physics switches are specialised on the values the reference
  * hard-codes (cloudsc_c.c:367-382: iwarmrain=2, ievaprain=2, ievapsnow=1, idepice=1) and on
  * laer*=false; cloudsc_b200_set_params() refuses any other parameter set.
  */
@@ -33,10 +42,15 @@
 
 #include "cloudsc_consts.h"
 
+#ifndef CLOUDSC_STRICT
+#define CLOUDSC_STRICT 0
+#endif
+
 #if defined(__CUDACC__)
 #define CLOUDSC_FN __device__ __forceinline__
 #else
 #include <cmath>
+#include <cstring>
 #define CLOUDSC_FN static inline
 #endif
 
@@ -60,11 +74,14 @@ enum OutSlot {
 };
 
 /* ---- math wrappers: same names for double/float, host/device -------------------------------- */
-template <typename T> CLOUDSC_FN T mx(T a, T b) { return fmax(a, b); }
-template <typename T> CLOUDSC_FN T mn(T a, T b) { return fmin(a, b); }
+/* max/min as compare+select.  For the NaN-free values of this scheme they return what
+ * fmax/fmin return (zeros of either sign compare equal), at 3 instead of 7 instructions on
+ * sm_100a (there is no DMNMX; fmax() expands to a NaN-aware sequence). */
+template <typename T> CLOUDSC_FN T mx(T a, T b) { return a > b ? a : b; }
+template <typename T> CLOUDSC_FN T mn(T a, T b) { return a < b ? a : b; }
 #if defined(__CUDACC__)
-CLOUDSC_FN double ex(double x) { return exp(x); }
-CLOUDSC_FN float ex(float x) { return expf(x); }
+CLOUDSC_FN double ex_lib(double x) { return exp(x); }
+CLOUDSC_FN float ex_lib(float x) { return expf(x); }
 CLOUDSC_FN double pw(double x, double y) { return pow(x, y); }
 CLOUDSC_FN float pw(float x, float y) { return powf(x, y); }
 CLOUDSC_FN double sq(double x) { return sqrt(x); }
@@ -74,8 +91,8 @@ CLOUDSC_FN float ab(float x) { return fabsf(x); }
 CLOUDSC_FN double cs(double x, double y) { return copysign(x, y); }
 CLOUDSC_FN float cs(float x, float y) { return copysignf(x, y); }
 #else
-static inline double ex(double x) { return std::exp(x); }
-static inline float ex(float x) { return std::exp(x); }
+static inline double ex_lib(double x) { return std::exp(x); }
+static inline float ex_lib(float x) { return std::exp(x); }
 static inline double pw(double x, double y) { return std::pow(x, y); }
 static inline float pw(float x, float y) { return std::pow(x, y); }
 static inline double sq(double x) { return std::sqrt(x); }
@@ -84,6 +101,77 @@ static inline double ab(double x) { return std::fabs(x); }
 static inline float ab(float x) { return std::fabs(x); }
 static inline double cs(double x, double y) { return std::copysign(x, y); }
 static inline float cs(float x, float y) { return std::copysign(x, y); }
+#endif
+
+/* ---- fast-mode primitives -------------------------------------------------------------------- */
+/*
+ * exp(x) without the library's special-case handling: x is clamped to [-700, 700] (every call
+ * site of the scheme is far inside; exp(-x^2) of the snow autoconversion underflows harmlessly to
+ * 1e-304 instead of 0), n = rint(x*log2 e), r = x - n ln2 (two-constant Cody-Waite), degree-12
+ * polynomial on |r| <= ln2/2 (fitted in extended precision, max rel. error 1.5e-16), scaling by
+ * adding n to the exponent field.  ~22 instructions instead of ~66.
+ */
+CLOUDSC_FN double exp_fast(double x) {
+  x = mn(mx(x, -700.0), 700.0);
+  const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
+  const double t = x * 1.4426950408889634 + magic;
+  const double fn = t - magic;
+  double r = fn * -6.93147180369123816490e-01 + x;
+  r = fn * -1.90821492927058770002e-10 + r;
+  double p = 2.09172269697194e-09;
+  p = p * r + 2.5105361442549964e-08;
+  p = p * r + 2.7557266270270763e-07;
+  p = p * r + 2.7557255115742253e-06;
+  p = p * r + 2.480158733369391e-05;
+  p = p * r + 0.0001984126987497067;
+  p = p * r + 0.0013888888888879635;
+  p = p * r + 0.00833333333332612;
+  p = p * r + 0.04166666666666668;
+  p = p * r + 0.1666666666666667;
+  p = p * r + 0.5;
+  p = p * r + 1.0;
+  p = p * r + 1.0;
+#if defined(__CUDACC__)
+  const int n = __double2loint(t);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+#else
+  long long tb, pb;
+  std::memcpy(&tb, &t, 8);
+  std::memcpy(&pb, &p, 8);
+  pb += (long long)(int)(tb & 0xffffffffLL) << 52;
+  std::memcpy(&p, &pb, 8);
+  return p;
+#endif
+}
+CLOUDSC_FN float exp_fast(float x) { return ex_lib(x); }
+
+/* 1/x by the hardware seed + two Newton steps, no zero/inf/denormal path (every divisor of the
+ * scheme is a normal number bounded away from 0 by an explicit max(., eps) or by its physics). */
+CLOUDSC_FN double rcp_fast(double x) {
+#if defined(__CUDACC__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+CLOUDSC_FN float rcp_fast(float x) { return 1.0f / x; }
+
+#if CLOUDSC_STRICT
+#define CLOUDSC_RCP(x) (one / (x))
+#define CLOUDSC_DIV(a, b) ((a) / (b))
+#define CLOUDSC_DIVR(a, b, r) ((a) / (b))  /* a/b where r == 1/b is available in fast mode */
+template <typename T> CLOUDSC_FN T ex(T x) { return ex_lib(x); }
+#else
+#define CLOUDSC_RCP(x) rcp_fast(x)
+#define CLOUDSC_DIV(a, b) ((a) * rcp_fast(b))
+#define CLOUDSC_DIVR(a, b, r) ((a) * (r))
+template <typename T> CLOUDSC_FN T ex(T x) { return exp_fast(x); }
 #endif
 
 /* State carried from level k-1 to level k (what "k-caching" keeps in registers) */
@@ -103,35 +191,34 @@ struct Carry {
   T fsqlf, fsqif, fcqlng, fcqnng, fsqltur, fsqitur; /* running flux sums :2548-2568 */
 };
 
-/* FOEALFA / FOEEWM pieces (cloudsc_c.c:335-351, inlined by the reference at every use) */
+/* FOEALFA / FOELDCPM (cloudsc_c.c:335-345, inlined by the reference at every use) */
 template <typename T>
 CLOUDSC_FN T foealfa(const CloudscConst<T> &c, T t) {
   const T x = (mx(c.rtice, mn(c.rtwat, t)) - c.rtice) * c.rtwat_rtice_r;
   return mn(T(1.0), x * x);
 }
 template <typename T>
-CLOUDSC_FN T exp_liq(const CloudscConst<T> &c, T t) { return ex((c.r3les * (t - c.rtt)) / (t - c.r4les)); }
-template <typename T>
-CLOUDSC_FN T exp_ice(const CloudscConst<T> &c, T t) { return ex((c.r3ies * (t - c.rtt)) / (t - c.r4ies)); }
-template <typename T>
-CLOUDSC_FN T foedem(const CloudscConst<T> &c, T t, T al) {
-  const T dl = t - c.r4les, di = t - c.r4ies;
-  return (al * c.r5alvcp) * (T(1.0) / (dl * dl)) + ((T(1.0) - al) * c.r5alscp) * (T(1.0) / (di * di));
-}
-template <typename T>
 CLOUDSC_FN T foeldcpm(const CloudscConst<T> &c, T al) { return al * c.ralvdcp + (T(1.0) - al) * c.ralsdcp; }
 
-/*
- * One Newton step of the saturation adjustment, cloudsc_c.c:1162-1168 (and :1169-1175).
- */
+/* One Newton step of the saturation adjustment, cloudsc_c.c:1162-1168 (and :1169-1175). */
 template <typename T>
 CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
+  const T one = T(1.0);
   const T al = foealfa(c, tn);
-  T qsat = (c.r2es * (al * exp_liq(c, tn) + (T(1.0) - al) * exp_ice(c, tn))) * qp;
+  const T dl = tn - c.r4les, di = tn - c.r4ies;
+  const T rdl = CLOUDSC_RCP(dl), rdi = CLOUDSC_RCP(di);
+  const T el = ex(CLOUDSC_DIVR(c.r3les * (tn - c.rtt), dl, rdl));
+  const T ei = ex(CLOUDSC_DIVR(c.r3ies * (tn - c.rtt), di, rdi));
+  T qsat = (c.r2es * (al * el + (one - al) * ei)) * qp;
   qsat = mn(T(0.5), qsat);
-  const T cor = T(1.0) / (T(1.0) - c.retv * qsat);
+  const T cor = CLOUDSC_RCP(one - c.retv * qsat);
   qsat = qsat * cor;
-  const T cond = (qsm - qsat) / (T(1.0) + (qsat * cor) * foedem(c, tn, al));
+#if CLOUDSC_STRICT
+  const T dem = (al * c.r5alvcp) * (one / (dl * dl)) + ((one - al) * c.r5alscp) * (one / (di * di)); /* FOEDEM */
+#else
+  const T dem = (al * c.r5alvcp) * (rdl * rdl) + ((one - al) * c.r5alscp) * (rdi * rdi);
+#endif
+  const T cond = CLOUDSC_DIV(qsm - qsat, one + (qsat * cor) * dem);
   tn = tn + foeldcpm(c, al) * cond;
   qsm = qsm - cond;
 }
@@ -141,24 +228,22 @@ CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
  *   template<int S> T ld(int k) const;        input slot S at level k (0-based; IN_PAPH: row k)
  *   template<int S> void st(int k, T v);      output slot S at row k
  *   T plsm() const; int ktype() const; void st_rainfrac(T);
+ *   void level_begin(int k); void level_end(int k);   hooks for staged IO (may be empty)
  */
 template <typename T, typename IO>
-CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev, const T ptsphy) {
+CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc, IO &io, const int klev) {
   const T zero = T(0.0), one = T(1.0);
-  const T zepsec = T(1.0e-14);
-  const T zepsilon = T(100.0) * (sizeof(T) == 8 ? T(2.220446049250313e-16) : T(1.1920929e-07f)); /* :360 */
-  /* cloudsc_c.c:385-391 */
-  const T zqtmst = one / ptsphy;
-  const T zrdcp = c.rd / c.rcpd;
-  const T zrg_r = one / c.rg;
-  const T zrldcp = one / (c.ralsdcp - c.ralvdcp);
-  /* wet-bulb fit constants, cloudsc_c.c:266-270 */
-  const T ztw1 = T(1329.31), ztw2 = T(0.0074615), ztw3 = T(0.85e5), ztw4 = T(40.637), ztw5 = T(275.0);
+  const T ptsphy = sc.ptsphy;
+  const T zqtmst = sc.zqtmst;
+  /* wet-bulb fit constants with exact binary64 high words, cloudsc_c.c:268,270 */
+  const T ztw3 = T(0.85e5), ztw5 = T(275.0);
 
   const int ktop = c.ncldtop - 1; /* first level (0-based) of the physics sweep, :732 */
 
   /* per-column constants */
   const T paph_surf = io.template ld<IN_PAPH>(klev); /* paph[klev+1] :1260,2064 */
+  const T r_paph_surf = CLOUDSC_RCP(paph_surf);
+  (void)r_paph_surf;
   const T plsm = io.plsm();
   const int ktype = io.ktype();
   /* cloudsc_c.c:1710-1717 */
@@ -186,6 +271,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
   io.template st<OUT_FHPSL>(0, -c.rlvtt * zero); io.template st<OUT_FHPSN>(0, -c.rlstt * zero);
 
   for (int k = 0; k < klev; ++k) {
+    io.level_begin(k);
     /* ================= 1. initial values of this level, :462-485 ========================== */
     const T pap = io.template ld<IN_PAP>(k);
     const T paph_n = io.template ld<IN_PAPH>(k + 1);
@@ -231,22 +317,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       }
     }
 
-    /* ---- saturation values, :588-603 */
-    const T alfa_w = foealfa(c, t);                 /* zfoealfa */
-    const T e_liq = exp_liq(c, t), e_ice = exp_ice(c, t);
-    const T foeewmt = mn((c.r2es * (alfa_w * e_liq + (one - alfa_w) * e_ice)) / pap, T(0.5));
-    const T qsmix = foeewmt / (one - c.retv * foeewmt);
-    const T zalfa = mx(zero, cs(one, t - c.rtt));
-    T foeew = mn((zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice)) / pap, T(0.5));
-    foeew = mn(T(0.5), foeew);
-    const T qsice = foeew / (one - c.retv * foeew);
-    const T foeeliqt = mn((c.r2es * e_liq) / pap, T(0.5));
-    const T qsliq = foeeliqt / (one - c.retv * foeeliqt);
-    /* ---- cloud fraction in [0,1]; liquid/ice fractions, :625-636 */
+    /* ---- FOEALFA of this level (:588; also needed by the flux section at every level) */
+    const T alfa_w = foealfa(c, t);
+    /* ---- cloud fraction in [0,1], :625 */
     a = mx(zero, mn(one, a));
-    const T li = qx[0] + qx[1];
-    T liqfrac = zero, icefrac = zero;
-    if (li > c.rlmin) { liqfrac = qx[0] / li; icefrac = one - liqfrac; }
 
     /* values of this level the flux section needs (zqxn2d stays 0 above ncldtop, :503) */
     T qxn2d[4] = {zero, zero, zero, zero};
@@ -257,6 +331,29 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
     const T mf_n = (k + 1 < klev && k + 1 >= ktop) ? io.template ld<IN_PMFU>(k + 1) + io.template ld<IN_PMFD>(k + 1) : zero;
 
     if (k >= ktop) {
+      /* ================= saturation values of this level, :583-640 ======================== */
+      /* (the reference computes them for all levels; above ncldtop only zfoealfa is ever read) */
+      const T dl = t - c.r4les, di = t - c.r4ies;
+      const T r_dl = CLOUDSC_RCP(dl), r_di = CLOUDSC_RCP(di);
+      const T r_pap = CLOUDSC_RCP(pap);
+      const T e_liq = ex(CLOUDSC_DIVR(c.r3les * (t - c.rtt), dl, r_dl));
+      const T e_ice = ex(CLOUDSC_DIVR(c.r3ies * (t - c.rtt), di, r_di));
+      const T foeewmt = mn(CLOUDSC_DIVR(c.r2es * (alfa_w * e_liq + (one - alfa_w) * e_ice), pap, r_pap), T(0.5));
+      const T cor_m = CLOUDSC_RCP(one - c.retv * foeewmt);
+      const T qsmix = CLOUDSC_DIVR(foeewmt, one - c.retv * foeewmt, cor_m);
+      const T zalfa = mx(zero, cs(one, t - c.rtt));
+      T foeew = mn(CLOUDSC_DIVR(zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice), pap, r_pap), T(0.5));
+      foeew = mn(T(0.5), foeew);
+      const T cor_i = CLOUDSC_RCP(one - c.retv * foeew);
+      const T qsice = CLOUDSC_DIVR(foeew, one - c.retv * foeew, cor_i);
+      const T foeeliqt = mn(CLOUDSC_DIVR(c.r2es * e_liq, pap, r_pap), T(0.5));
+      const T cor_l = CLOUDSC_RCP(one - c.retv * foeeliqt);
+      const T qsliq = CLOUDSC_DIVR(foeeliqt, one - c.retv * foeeliqt, cor_l);
+      /* liquid/ice fractions, :628-636 */
+      const T li = qx[0] + qx[1];
+      T liqfrac = zero, icefrac = zero;
+      if (li > c.rlmin) { liqfrac = CLOUDSC_DIV(qx[0], li); icefrac = one - liqfrac; }
+
       /* ================= 3.0 initialise, :739-859 ========================================= */
       T qxfg[4] = {qx[0], qx[1], qx[2], qx[3]};
       T qa[5][5], qb03 = zero, qb13 = zero, qb00 = zero, qb11 = zero;
@@ -269,60 +366,73 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       T convsink = zero; /* zconvsink[l] == zconvsink[i] */
 
       const T dp = paph_n - s.paph_k;
-      const T gdp = c.rg / dp;
+      const T r_dp = CLOUDSC_RCP(dp);
+      const T gdp = CLOUDSC_DIVR(c.rg, dp, r_dp);
+#if CLOUDSC_STRICT
       const T rho = pap / (c.rd * t);
+      const T r_rho = one / rho;
+#else
+      const T r_t = rcp_fast(t);
+      const T rho = (pap * c.r_rd) * r_t;
+      const T r_rho = (c.rd * t) * r_pap;
+#endif
+      (void)r_rho;
       const T dtgdp = ptsphy * gdp;
-      const T rdtgdp = dp * (one / (ptsphy * c.rg));
-      /* dqs/dT correction factors, :818-834 */
-      const T dl = t - c.r4les, di = t - c.r4ies;
+      const T rdtgdp = dp * sc.r_ptsphy_rg;
+      /* dqs/dT correction factors, :818-834 (zcorqsliq/zevaplimliq/zevaplimice are never read) */
+#if CLOUDSC_STRICT
       const T facw = c.r5les / (dl * dl);
-      T cor = one / (one - c.retv * foeeliqt);
-      const T dqsliqdt = (facw * cor) * qsliq;
-      const T corqsliq = one + c.ralvdcp * dqsliqdt;
       const T faci = c.r5ies / (di * di);
-      cor = one / (one - c.retv * foeew);
-      const T dqsicedt = (faci * cor) * qsice;
+#else
+      const T facw = c.r5les * (r_dl * r_dl);
+      const T faci = c.r5ies * (r_di * r_di);
+#endif
+      const T dqsicedt = (faci * cor_i) * qsice;
       const T corqsice = one + c.ralsdcp * dqsicedt;
+      const T r_corqsice = CLOUDSC_RCP(corqsice);
+      (void)r_corqsice;
       const T facm = alfa_w * facw + (one - alfa_w) * faci;
-      cor = one / (one - c.retv * foeewmt);
-      const T dqsmixdt = (facm * cor) * qsmix;
+      const T dqsmixdt = (facm * cor_m) * qsmix;
       const T corqsmix = one + foeldcpm(c, alfa_w) * dqsmixdt;
-      const T evaplimmix = mx((qsmix - qv) / corqsmix, zero);
-      /* zevaplimliq (:833) is never read; zevaplimice only by the dead ievapsnow=2 branch */
-      (void)corqsliq;
+      const T evaplimmix = mx(CLOUDSC_DIV(qsmix - qv, corqsmix), zero);
+      (void)cor_l;
       /* in-cloud condensate, :837-840 */
-      T tmpa = one / mx(a, zepsec);
+      const T tmpa = CLOUDSC_RCP(mx(a, c.zepsec));
       T liqcld = qx[0] * tmpa;
       T icecld = qx[1] * tmpa;
-      T licld = liqcld + icecld;
+      const T licld = liqcld + icecld;
+      /* 1/max(eps, 1-a): :1278,1284,1321,1940,1990,2051,2053 */
+      const T one_m_a = one - a;
+      const T r_1ma = CLOUDSC_RCP(mx(c.zepsec, one_m_a));
+      (void)r_1ma;
 
       /* evaporate very small amounts of liquid and ice, :847-857 */
       if (qx[0] < c.rlmin) { qa[0][4] = qx[0]; qa[4][0] = -qx[0]; }
       if (qx[1] < c.rlmin) { qa[1][4] = qx[1]; qa[4][1] = -qx[1]; }
 
       /* ================= 3.1 ice supersaturation adjustment, :879-952 ===================== */
-      const T fokoop = mn(c.rkoop1 - c.rkoop2 * t, (c.r2es * e_liq) / (c.r2es * e_ice));
+      const T fokoop = mn(c.rkoop1 - c.rkoop2 * t, CLOUDSC_DIV(c.r2es * e_liq, c.r2es * e_ice));
       {
         T fac, facI;
         if (c.nssopt == 0 || t >= c.rtt) { fac = one; facI = one; }
-        else { fac = a + fokoop * (one - a); facI = ptsphy / c.rkooptau; }
+        else { fac = a + fokoop * one_m_a; facI = sc.faci_koop; }
         T supsat;
-        if (a > one - c.ramin) {
-          supsat = mx((qv - fac * qsice) / corqsice, zero);
+        if (a > sc.one_m_ramin) {
+          supsat = mx(CLOUDSC_DIVR(qv - fac * qsice, corqsice, r_corqsice), zero);
         } else {
-          const T qp1env = (qv - a * qsice) / mx(one - a, zepsilon);
-          supsat = mx(((one - a) * (qp1env - fac * qsice)) / corqsice, zero);
+          const T qp1env = CLOUDSC_DIV(qv - a * qsice, mx(one_m_a, c.zepsilon));
+          supsat = mx(CLOUDSC_DIVR(one_m_a * (qp1env - fac * qsice), corqsice, r_corqsice), zero);
         }
-        if (supsat > zepsec) {
+        if (supsat > c.zepsec) {
           if (t > c.rthomo) { qa[4][0] = qa[4][0] + supsat; qa[0][4] = qa[0][4] - supsat; qxfg[0] = qxfg[0] + supsat; }
           else              { qa[4][1] = qa[4][1] + supsat; qa[1][4] = qa[1][4] - supsat; qxfg[1] = qxfg[1] + supsat; }
-          solac = (one - a) * facI;
+          solac = one_m_a * facI;
         }
         const T psupsat = io.template ld<IN_PSUPSAT>(k);
-        if (psupsat > zepsec) {
+        if (psupsat > c.zepsec) {
           if (t > c.rthomo) { qa[0][0] = qa[0][0] + psupsat; psupsrce0 = psupsat; qxfg[0] = qxfg[0] + psupsat; }
           else              { qa[1][1] = qa[1][1] + psupsat; psupsrce1 = psupsat; qxfg[1] = qxfg[1] + psupsat; }
-          solac = (one - a) * facI;
+          solac = one_m_a * facI;
         }
       }
 
@@ -330,8 +440,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       if (k + 1 < klev) {
         const T plu_n = io.template ld<IN_PLU>(k + 1);
         plude_out = plude_out * dtgdp;
-        if (plu_n > zepsec && plude_out > c.rlmin) {
-          solac = solac + plude_out / plu_n;
+        if (plu_n > c.zepsec && plude_out > c.rlmin) {
+          solac = solac + CLOUDSC_DIV(plude_out, plu_n);
           convsrce0 = alfa_w * plude_out;
           convsrce1 = (one - alfa_w) * plude_out;
           qa[0][0] = qa[0][0] + convsrce0;
@@ -350,7 +460,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
         const T lcust0 = mf * s.qlnm1, lcust1 = mf * s.qinm1;
         convsrce0 = convsrce0 + lcust0;
         convsrce1 = convsrce1 + lcust1;
-        const T dtdp = ((zrdcp * T(0.5)) * (s.tp1_m1 + t)) / s.paph_k;
+        const T dtdp = CLOUDSC_DIV(sc.zrdcp_half * (s.tp1_m1 + t), s.paph_k);
         const T dtforc = dtdp * (pap - s.pap_m1);
         const T dqs_s = (s.anewm1 * dtforc) * dqsmixdt;
         T lfinalsum = zero;
@@ -366,7 +476,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
           lfinalsum = lfinalsum + lfinal;
           qa[1][1] = qa[1][1] + lcust1; qa[1][4] = qa[1][4] + evap; qa[4][1] = qa[4][1] - evap;
         }
-        if (lfinalsum < zepsec) acust = zero;
+        if (lfinalsum < c.zepsec) acust = zero;
         solac = solac + acust;
       }
       if (k + 1 < klev) { /* subsidence sink, :1064-1075 */
@@ -379,14 +489,13 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
 
       /* ================= 3.4 erosion of clouds by turbulent mixing, :1087-1118 ============ */
       {
-        T ldifdt = c.rcldiff * ptsphy;
-        if (ktype > 0 && plude_out > zepsec) ldifdt = c.rcldiff_convi * ldifdt;
-        if (li > zepsec) {
+        const T ldifdt = (ktype > 0 && plude_out > c.zepsec) ? sc.ldifdt_conv : sc.ldifdt;
+        if (li > c.zepsec) {
           const T e = ldifdt * mx(qsmix - qv, zero);
           T leros = a * e;
           leros = mn(leros, evaplimmix);
           leros = mn(leros, li);
-          const T aeros = leros / licld;
+          const T aeros = CLOUDSC_DIV(leros, licld);
           solac = solac - aeros;
           qa[0][4] = qa[0][4] + liqfrac * leros; qa[4][0] = qa[4][0] - liqfrac * leros;
           qa[1][4] = qa[1][4] + icefrac * leros; qa[4][1] = qa[4][1] - icefrac * leros;
@@ -396,20 +505,19 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       /* ================= 3.4 condensation/evaporation due to dqsat/dT, :1137-1182 ========= */
       T dqs;
       {
-        const T dtdp = (zrdcp * t) / pap;
+        const T dtdp = CLOUDSC_DIVR(sc.zrdcp * t, pap, r_pap);
         const T dpmxdt = dp * zqtmst;
         const T mfdn = (k + 1 < klev) ? mf_n : zero;
-        T wtot = io.template ld<IN_PVERVEL>(k) + (T(0.5) * c.rg) * (s.mf_k + mfdn);
+        T wtot = io.template ld<IN_PVERVEL>(k) + sc.half_rg * (s.mf_k + mfdn);
         wtot = mn(dpmxdt, mx(-dpmxdt, wtot));
         const T zzzdt = io.template ld<IN_PHRSW>(k) + io.template ld<IN_PHRLW>(k);
         const T dtdiab = mn(dpmxdt * dtdp, mx(-dpmxdt * dtdp, zzzdt)) * ptsphy; /* + ralfdcp*zldefr, zldefr == 0 */
         const T dtforc = (dtdp * wtot) * ptsphy + dtdiab;
         T tn = t + dtforc;
         tn = mx(tn, T(160.0));
-        const T qp = one / pap;
         T qsm = qsmix;
-        satadj_step(c, qp, tn, qsm);
-        satadj_step(c, qp, tn, qsm);
+        satadj_step(c, r_pap, tn, qsm);
+        satadj_step(c, r_pap, tn, qsm);
         dqs = qsm - qsmix;
       }
       /* 3.4a evaporation of clouds, :1191-1205 */
@@ -421,14 +529,19 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
         qa[1][4] = qa[1][4] + icefrac * levap; qa[4][1] = qa[4][1] - icefrac * levap;
       }
       /* 3.4b (1) increase of cloud water in existing clouds, :1214-1248 */
-      if (dqs <= -c.rlmin && a > zepsec) {
+      if (dqs <= -c.rlmin && a > c.zepsec) {
         T lcond1 = mx(-dqs, zero);
         T cdmax;
-        if (a > T(0.99)) {
-          const T corm = one / (one - c.retv * qsmix);
-          cdmax = (qv - qsmix) / (one + (corm * qsmix) * foedem(c, t, alfa_w));
+        if (a > c.p099) {
+          const T corm = CLOUDSC_RCP(one - c.retv * qsmix);
+#if CLOUDSC_STRICT
+          const T dem = (alfa_w * c.r5alvcp) * (one / (dl * dl)) + ((one - alfa_w) * c.r5alscp) * (one / (di * di));
+#else
+          const T dem = (alfa_w * c.r5alvcp) * (r_dl * r_dl) + ((one - alfa_w) * c.r5alscp) * (r_di * r_di);
+#endif
+          cdmax = CLOUDSC_DIV(qv - qsmix, one + (corm * qsmix) * dem);
         } else {
-          cdmax = (qv - a * qsmix) / a;
+          cdmax = CLOUDSC_DIV(qv - a * qsmix, a);
         }
         lcond1 = mx(mn(lcond1, cdmax), zero);
         lcond1 = a * lcond1;
@@ -437,13 +550,13 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
         else              { qa[4][1] = qa[4][1] + lcond1; qa[1][4] = qa[1][4] - lcond1; qxfg[1] = qxfg[1] + lcond1; }
       }
       /* 3.4b (2) generation of new clouds, :1254-1361 */
-      if (dqs <= -c.rlmin && a < one - zepsec) {
+      if (dqs <= -c.rlmin && a < sc.one_m_zepsec) {
         T rhc = c.ramid;
-        const T sigk = pap / paph_surf;
-        if (sigk > T(0.8)) { const T x = (sigk - T(0.8)) / T(0.2); rhc = c.ramid + (one - c.ramid) * (x * x); }
+        const T sigk = CLOUDSC_DIVR(pap, paph_surf, r_paph_surf);
+        if (sigk > c.p08) { const T x = CLOUDSC_DIVR(sigk - c.p08, c.p02, c.r_p02); rhc = c.ramid + sc.one_m_ramid * (x * x); }
         T qe;
         if (c.nssopt == 0 || c.nssopt == 1) {
-          qe = (qv - a * qsice) / mx(zepsec, one - a);
+          qe = CLOUDSC_DIVR(qv - a * qsice, mx(c.zepsec, one_m_a), r_1ma);
           qe = mx(zero, qe);
         } else if (c.nssopt == 2) {
           qe = qv;
@@ -452,16 +565,16 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
         }
         const T fac = (c.nssopt == 0 || t >= c.rtt) ? one : fokoop;
         if (qe >= qsice * fac * rhc && qe < qsice * fac) {
-          T acond = (-((one - a) * fac) * dqs) / mx(T(2.0) * (fac * qsice - qe), zepsec);
-          acond = mn(acond, one - a);
+          T acond = CLOUDSC_DIV(-(one_m_a * fac) * dqs, mx(T(2.0) * (fac * qsice - qe), c.zepsec));
+          acond = mn(acond, one_m_a);
           T lcond2 = (-(fac * dqs) * T(0.5)) * acond;
-          const T zdl = (T(2.0) * (fac * qsice - qe)) / mx(zepsec, one - a);
+          const T zdl = CLOUDSC_DIVR(T(2.0) * (fac * qsice - qe), mx(c.zepsec, one_m_a), r_1ma);
           if (dqs * fac < -zdl) {
             const T lcondlim = ((a - one) * fac) * dqs - fac * qsice + qv;
             lcond2 = mn(lcond2, lcondlim);
           }
           lcond2 = mx(lcond2, zero);
-          if (one - a < zepsec || lcond2 < c.rlmin) { lcond2 = zero; acond = zero; }
+          if (one_m_a < c.zepsec || lcond2 < c.rlmin) { lcond2 = zero; acond = zero; }
           if (lcond2 == zero) acond = zero;
           solac = solac + acond;
           if (t > c.rthomo) { qa[4][0] = qa[4][0] + lcond2; qa[0][4] = qa[0][4] - lcond2; qxfg[0] = qxfg[0] + lcond2; }
@@ -471,30 +584,39 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
 
       /* ================= 3.7 growth of ice by vapour deposition (Rotstayn), :1384-1447 ==== */
       if (a >= c.rcldtopcf && s.a_m1 < c.rcldtopcf) s.cldtopdist = zero;
+#if CLOUDSC_STRICT
       else s.cldtopdist = s.cldtopdist + dp / (rho * c.rg);
+#else
+      else s.cldtopdist = s.cldtopdist + (dp * r_rho) * sc.zrg_r;
+#endif
       if (qxfg[0] > c.rlmin && t < c.rtt) {
-        const T vpice = ((c.r2es * e_ice) * c.rv) / c.rd;
+        const T vpice = CLOUDSC_DIVR((c.r2es * e_ice) * c.rv, c.rd, c.r_rd);
         const T vpliq = vpice * fokoop;
-        const T icenuclei = T(1000.0) * ex((T(12.96) * (vpliq - vpice)) / vpliq - T(0.639));
-        const T add = (c.rlstt * (c.rlstt / (c.rv * t) - one)) / (T(0.024) * t);
-        const T bdd = ((c.rv * t) * pap) / (T(2.21) * vpice);
-        const T cvds = ((T(7.8) * pw(icenuclei / rho, T(0.666))) * (vpliq - vpice)) / ((T(8.87) * (add + bdd)) * vpice);
+        const T icenuclei = T(1000.0) * ex(CLOUDSC_DIV(c.p1296 * (vpliq - vpice), vpliq) - c.p0639);
+#if CLOUDSC_STRICT
+        const T add = (c.rlstt * (c.rlstt / (c.rv * t) - one)) / (c.p0024 * t);
+        const T bdd = ((c.rv * t) * pap) / (c.p221 * vpice);
+        const T cvds = ((c.p78 * pw(icenuclei / rho, c.p0666)) * (vpliq - vpice)) / ((c.p887 * (add + bdd)) * vpice);
         const T ice0 = mx(icecld, (icenuclei * c.riceinit) / rho);
-        const T inew = pw((T(0.666) * cvds) * ptsphy + pw(ice0, T(0.666)), T(1.5));
+#else
+        const T add = (c.rlstt * ((c.rlstt * c.r_rv) * r_t - one)) * (c.r_p0024 * r_t);
+        const T bdd = ((c.rv * t) * pap) * rcp_fast(c.p221 * vpice);
+        const T cvds = ((c.p78 * pw(icenuclei * r_rho, c.p0666)) * (vpliq - vpice)) * rcp_fast((c.p887 * (add + bdd)) * vpice);
+        const T ice0 = mx(icecld, (icenuclei * c.riceinit) * r_rho);
+#endif
+        const T inew = pw((c.p0666 * cvds) * ptsphy + pw(ice0, c.p0666), T(1.5));
         T depos = mx(a * (inew - ice0), zero);
         depos = mn(depos, qxfg[0]);
-        const T infactor = mn(icenuclei / T(15000.0), one);
-        depos = depos * mn(infactor + (one - infactor) * (c.rdepliqrefrate + s.cldtopdist / c.rdepliqrefdepth), one);
+        const T infactor = mn(CLOUDSC_DIVR(icenuclei, T(15000.0), c.r_15000), one);
+        depos = depos * mn(infactor + (one - infactor) * (c.rdepliqrefrate + CLOUDSC_DIVR(s.cldtopdist, c.rdepliqrefdepth, c.r_rdepliqrefdepth)), one);
         qa[0][1] = qa[0][1] + depos; qa[1][0] = qa[1][0] - depos;
         qxfg[1] = qxfg[1] + depos; qxfg[0] = qxfg[0] - depos;
       }
 
       /* ================= 4. precipitation processes ====================================== */
-      tmpa = one / mx(a, zepsec);                      /* :1529-1532 */
+      /* revised in-cloud condensate :1529-1532 (same 1/max(a,eps) as :837) */
       liqcld = qxfg[0] * tmpa;
       icecld = qxfg[1] * tmpa;
-      licld = liqcld + icecld;
-      (void)licld;
 
       /* 4.2 sedimentation, :1541-1576 (species i, r, s; llfall = r,s plus ice) */
       T qpretot = zero;
@@ -510,12 +632,14 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
 
       /* precipitation cover, max-random overlap, :1595-1609 */
       T covpclr, raincld, snowcld;
-      if (qpretot > zepsec) {
-        s.covptot = one - ((one - s.covptot) * (one - mx(a, s.a_m1))) / (one - mn(s.a_m1, one - T(1.0e-6)));
+      if (qpretot > c.zepsec) {
+        s.covptot = one - CLOUDSC_DIV((one - s.covptot) * (one - mx(a, s.a_m1)), one - mn(s.a_m1, c.one_m_1em6));
         s.covptot = mx(s.covptot, c.rcovpmin);
         covpclr = mx(zero, s.covptot - a);
-        raincld = qxfg[2] / s.covptot;
-        snowcld = qxfg[3] / s.covptot;
+        const T r_cov = CLOUDSC_RCP(s.covptot);
+        (void)r_cov;
+        raincld = CLOUDSC_DIVR(qxfg[2], s.covptot, r_cov);
+        snowcld = CLOUDSC_DIVR(qxfg[3], s.covptot, r_cov);
         s.covpmax = mx(s.covptot, s.covpmax);
       } else {
         raincld = zero; snowcld = zero; s.covptot = zero; covpclr = zero; s.covpmax = zero;
@@ -523,23 +647,23 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
 
       /* 4.3a autoconversion to snow, :1617-1637 */
       if (t <= c.rtt) {
-        if (icecld > zepsec) {
-          const T zco = (ptsphy * c.rsnowlin1) * ex(c.rsnowlin2 * (t - c.rtt));
-          const T x = icecld / c.rlcritsnow;
+        if (icecld > c.zepsec) {
+          const T zco = sc.snowlin * ex(c.rsnowlin2 * (t - c.rtt));
+          const T x = CLOUDSC_DIVR(icecld, c.rlcritsnow, c.r_rlcritsnow);
           const T snowaut = zco * (one - ex(-(x * x)));
           qb13 = qb13 + snowaut;
         }
       }
       /* 4.3b warm-rain autoconversion + accretion, Khairoutdinov-Kogan, :1644-1759 */
-      if (liqcld > zepsec) {
+      if (liqcld > c.zepsec) {
         T rainaut, rainacc;
         if (liqcld > lcrit_kk) {
           rainaut = ((((T(1.5) * a) * ptsphy) * c.rcl_kkaau) * pw(liqcld, c.rcl_kkbauq)) * kk_num_pow;
           rainaut = mn(rainaut, qxfg[0]);
-          if (rainaut < zepsec) rainaut = zero;
+          if (rainaut < c.zepsec) rainaut = zero;
           rainacc = (((T(2.0) * a) * ptsphy) * c.rcl_kkaac) * pw(liqcld * raincld, c.rcl_kkbac);
           rainacc = mn(rainacc, qxfg[0]);
-          if (rainacc < zepsec) rainacc = zero;
+          if (rainacc < c.zepsec) rainacc = zero;
         } else {
           rainaut = zero; rainacc = zero;
         }
@@ -552,10 +676,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
         }
       }
       /* riming of snow by cloud water, :1771-1785 */
-      if (t <= c.rtt && liqcld > zepsec) {
-        if (s.covptot > T(0.01) && snowcld > zepsec) {
-          const T fallcorr = pw(c.rdensref / rho, T(0.4));
-          T snowrime = ((((T(0.3) * s.covptot) * ptsphy) * c.rcl_const7s) * fallcorr) *
+      if (t <= c.rtt && liqcld > c.zepsec) {
+        if (s.covptot > c.p001 && snowcld > c.zepsec) {
+          const T fallcorr = pw(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
+          T snowrime = ((((c.p03 * s.covptot) * ptsphy) * c.rcl_const7s) * fallcorr) *
                        pw((rho * snowcld) * c.rcl_const1s, c.rcl_const8s);
           snowrime = mn(snowrime, one);
           qb03 = qb03 + snowrime;
@@ -566,41 +690,43 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       {
         const T icetot = qxfg[1] + qxfg[3];
         T meltmax = zero;
-        if (icetot > zepsec && t > c.rtt) {
+        if (icetot > c.zepsec && t > c.rtt) {
           const T subsat = mx(qsice - qv, zero);
-          const T tdmtw0 = t - c.rtt - subsat * (ztw1 + ztw2 * (pap - ztw3) - ztw4 * (t - ztw5));
-          const T cons1 = ab((ptsphy * (one + T(0.5) * tdmtw0)) / c.rtaumel);
-          meltmax = mx((tdmtw0 * cons1) * zrldcp, zero);
+          const T tdmtw0 = t - c.rtt - subsat * (c.ztw1 + c.ztw2 * (pap - ztw3) - c.ztw4 * (t - ztw5));
+          const T cons1 = ab(CLOUDSC_DIVR(ptsphy * (one + T(0.5) * tdmtw0), c.rtaumel, c.r_rtaumel));
+          meltmax = mx((tdmtw0 * cons1) * sc.zrldcp, zero);
         }
-        if (icetot > zepsec && meltmax > zepsec) {
-          T alfa = qxfg[1] / icetot;
+        if (icetot > c.zepsec && meltmax > c.zepsec) {
+          const T r_icetot = CLOUDSC_RCP(icetot);
+          (void)r_icetot;
+          T alfa = CLOUDSC_DIVR(qxfg[1], icetot, r_icetot);
           T melt = mn(qxfg[1], alfa * meltmax);
           qxfg[1] = qxfg[1] - melt; qxfg[2] = qxfg[2] + melt;
           qa[1][2] = qa[1][2] + melt; qa[2][1] = qa[2][1] - melt;
-          alfa = qxfg[3] / icetot;
+          alfa = CLOUDSC_DIVR(qxfg[3], icetot, r_icetot);
           melt = mn(qxfg[3], alfa * meltmax);
           qxfg[3] = qxfg[3] - melt; qxfg[2] = qxfg[2] + melt;
           qa[3][2] = qa[3][2] + melt; qa[2][3] = qa[2][3] - melt;
         }
       }
       /* 4.4b freezing of rain, :1866-1906 */
-      if (qx[2] > zepsec) {
+      if (qx[2] > c.zepsec) {
         if (t <= c.rtt && s.tp1_m1 > c.rtt) {
-          const T qpre = mx(qx[3] + qx[2], zepsec);
-          s.rainfrac = qx[2] / qpre;
+          const T qpre = mx(qx[3] + qx[2], c.zepsec);
+          s.rainfrac = CLOUDSC_DIV(qx[2], qpre);
         }
         if (t < c.rtt) {
           T frzmax;
-          if (s.rainfrac > T(0.8)) {
-            const T lambda = pw(c.rcl_fac1 / (rho * qx[2]), c.rcl_fac2);
+          if (s.rainfrac > c.p08) {
+            const T lambda = pw(CLOUDSC_DIV(c.rcl_fac1, rho * qx[2]), c.rcl_fac2);
             const T temp = c.rcl_fzrab * (t - c.rtt);
-            const T frz = ((ptsphy * (c.rcl_const5r / rho)) * (ex(temp) - one)) * pw(lambda, c.rcl_const6r);
+            const T frz = ((ptsphy * CLOUDSC_DIVR(c.rcl_const5r, rho, r_rho)) * (ex(temp) - one)) * pw(lambda, c.rcl_const6r);
             frzmax = mx(frz, zero);
           } else {
-            const T cons1 = ab((ptsphy * (one + T(0.5) * (c.rtt - t))) / c.rtaumel);
-            frzmax = mx(((c.rtt - t) * cons1) * zrldcp, zero);
+            const T cons1 = ab(CLOUDSC_DIVR(ptsphy * (one + T(0.5) * (c.rtt - t)), c.rtaumel, c.r_rtaumel));
+            frzmax = mx(((c.rtt - t) * cons1) * sc.zrldcp, zero);
           }
-          if (frzmax > zepsec) {
+          if (frzmax > c.zepsec) {
             const T frz = mn(qx[2], frzmax);
             qa[2][3] = qa[2][3] + frz; qa[3][2] = qa[3][2] - frz;
           }
@@ -608,54 +734,54 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       }
       /* 4.4c freezing of liquid, :1913-1928 */
       {
-        const T frzmax = mx((c.rthomo - t) * zrldcp, zero);
-        if (frzmax > zepsec && qxfg[0] > zepsec) {
+        const T frzmax = mx((c.rthomo - t) * sc.zrldcp, zero);
+        if (frzmax > c.zepsec && qxfg[0] > c.zepsec) {
           const T frz = mn(qxfg[0], frzmax);
           qa[0][1] = qa[0][1] + frz; qa[1][0] = qa[1][0] - frz;
         }
       }
       /* 4.5 evaporation of rain, Abel & Boutle, :1984-2038 */
+      /* zzrh0 is shared by the rain and snow branches, :1990-1991 == :2051-2052 */
+      T zzrh0 = c.rprecrhmax + CLOUDSC_DIVR(sc.one_m_rprecrhmax * s.covpmax, mx(c.zepsec, one_m_a), r_1ma);
+      zzrh0 = mn(mx(zzrh0, c.rprecrhmax), one);
       {
-        T zzrh = c.rprecrhmax + ((one - c.rprecrhmax) * s.covpmax) / mx(zepsec, one - a);
-        zzrh = mn(mx(zzrh, c.rprecrhmax), one);
-        zzrh = mn(T(0.8), zzrh);
+        const T zzrh = mn(c.p08, zzrh0);
         const T qe = mx(zero, mn(qv, qsliq));
-        if (covpclr > zepsec && qxfg[2] > zepsec && qe < zzrh * qsliq) {
-          const T preclr = qxfg[2] / s.covptot;
-          const T fallcorr = pw(c.rdensref / rho, T(0.4));
-          const T esatliq = (c.rv / c.rd) * (c.r2es * e_liq);
-          const T lambda = pw(c.rcl_fac1 / (rho * preclr), c.rcl_fac2);
+        if (covpclr > c.zepsec && qxfg[2] > c.zepsec && qe < zzrh * qsliq) {
+          const T preclr = CLOUDSC_DIV(qxfg[2], s.covptot);
+          const T fallcorr = pw(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
+          const T esatliq = sc.rv_rd * (c.r2es * e_liq);
+          const T lambda = pw(CLOUDSC_DIV(c.rcl_fac1, rho * preclr), c.rcl_fac2);
           const T evap_denom = c.rcl_cdenom1 * esatliq - c.rcl_cdenom2 * t * esatliq + (c.rcl_cdenom3 * pw(t, T(3.0))) * pap;
-          const T corr2 = (pw(t / T(273.0), T(1.5)) * T(393.0)) / (t + T(120.0));
+          const T corr2 = CLOUDSC_DIV(pw(CLOUDSC_DIVR(t, T(273.0), c.r_273), T(1.5)) * T(393.0), t + T(120.0));
           const T subsat = mx(zzrh * qsliq - qe, zero);
-          const T beta = (((((T(0.5) / qsliq) * (t * t)) * esatliq) * c.rcl_const1r) * (corr2 / evap_denom)) *
-                         (T(0.78) / pw(lambda, c.rcl_const4r) +
-                          (c.rcl_const2r * sq(rho * fallcorr)) / (sq(corr2) * pw(lambda, c.rcl_const3r)));
+          const T beta = ((((CLOUDSC_DIV(T(0.5), qsliq) * (t * t)) * esatliq) * c.rcl_const1r) * CLOUDSC_DIV(corr2, evap_denom)) *
+                         (CLOUDSC_DIV(c.p078, pw(lambda, c.rcl_const4r)) +
+                          CLOUDSC_DIV(c.rcl_const2r * sq(rho * fallcorr), sq(corr2) * pw(lambda, c.rcl_const3r)));
           const T denom = one + beta * ptsphy;
-          const T dpevap = (((covpclr * beta) * ptsphy) * subsat) / denom;
+          const T dpevap = CLOUDSC_DIV(((covpclr * beta) * ptsphy) * subsat, denom);
           const T evap = mn(dpevap, qxfg[2]);
           qa[2][4] = qa[2][4] + evap; qa[4][2] = qa[4][2] - evap;
-          s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, ((s.covptot - a) * evap) / qxfg[2]));
+          s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, CLOUDSC_DIV((s.covptot - a) * evap, qxfg[2])));
           qxfg[2] = qxfg[2] - evap;
         }
       }
       /* 4.5 evaporation of snow, Sundqvist-type, :2050-2087 */
       {
-        T zzrh = c.rprecrhmax + ((one - c.rprecrhmax) * s.covpmax) / mx(zepsec, one - a);
-        zzrh = mn(mx(zzrh, c.rprecrhmax), one);
-        T qe = (qv - a * qsice) / mx(zepsec, one - a);
+        const T zzrh = zzrh0;
+        T qe = CLOUDSC_DIVR(qv - a * qsice, mx(c.zepsec, one_m_a), r_1ma);
         qe = mx(zero, mn(qe, qsice));
-        if (covpclr > zepsec && qxfg[3] > zepsec && qe < zzrh * qsice) {
+        if (covpclr > c.zepsec && qxfg[3] > c.zepsec && qe < zzrh * qsice) {
           const T cd = s.covptot * dtgdp;
-          const T preclr = (qxfg[3] * covpclr) / cs(mx(ab(cd), zepsilon), cd);
-          const T beta1 = ((sq(pap / paph_surf) / c.rvrfactor) * preclr) / mx(covpclr, zepsec);
-          const T beta = (c.rg * c.rpecons) * pw(beta1, T(0.5777));
+          const T preclr = CLOUDSC_DIV(qxfg[3] * covpclr, cs(mx(ab(cd), c.zepsilon), cd));
+          const T beta1 = CLOUDSC_DIV(CLOUDSC_DIVR(sq(CLOUDSC_DIVR(pap, paph_surf, r_paph_surf)), c.rvrfactor, c.r_rvrfactor) * preclr, mx(covpclr, c.zepsec));
+          const T beta = sc.rg_rpecons * pw(beta1, c.p05777);
           const T denom = one + (beta * ptsphy) * corqsice;
-          const T dpr = ((((covpclr * beta) * (qsice - qe)) / denom) * dp) * zrg_r;
+          const T dpr = (CLOUDSC_DIV((covpclr * beta) * (qsice - qe), denom) * dp) * sc.zrg_r;
           const T dpevap = dpr * dtgdp;
           const T evap = mn(dpevap, qxfg[3]);
           qa[3][4] = qa[3][4] + evap; qa[4][3] = qa[4][3] - evap;
-          s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, ((s.covptot - a) * evap) / qxfg[3]));
+          s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, CLOUDSC_DIV((s.covptot - a) * evap, qxfg[3])));
           qxfg[3] = qxfg[3] - evap;
         }
       }
@@ -664,14 +790,16 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       if (qxfg[3] < c.rlmin) { qa[3][4] = qa[3][4] + qxfg[3]; qa[4][3] = qa[4][3] - qxfg[3]; }
 
       /* ================= 5.1 solver for cloud cover, :2168-2180 =========================== */
-      T anew = (a + solac) / (one + solab);
+      T anew = CLOUDSC_DIV(a + solac, one + solab);
       anew = mn(anew, one);
       if (anew < c.ramin) anew = zero;
       const T da = anew - aorig;
       s.anewm1 = anew;
 
       /* ================= 5.2 sink limiter, :2233-2286 ===================================== */
-      /* (the first pass :2207-2227 is overwritten before use) */
+      /* (the first pass :2207-2227 is overwritten before use).  zratio = zmm/max(zsinksum,zmm) is
+       * exactly 1 unless the sinks of species m exceed its content, and scaling by 1 is the
+       * identity -- so the divide and the scaling only run in that case. */
       const T qx5[5] = {qx[0], qx[1], qx[2], qx[3], qv};
 #pragma unroll
       for (int m = 0; m < 5; ++m) {
@@ -679,14 +807,15 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
 #pragma unroll
         for (int n = 0; n < 5; ++n) psum = psum + qa[n][m];
         const T sinksum = zero - psum;
-        const T mm = mx(qx5[m], zepsec);
-        const T rr = mx(sinksum, mm);
-        const T ratio = mm / rr;
+        const T mm = mx(qx5[m], c.zepsec);
+        if (sinksum > mm) {
+          const T ratio = CLOUDSC_DIV(mm, sinksum);
 #pragma unroll
-        for (int n = 0; n < 5; ++n) {
-          if (qa[n][m] < zero) {
-            qa[n][m] = qa[n][m] * ratio;
-            qa[m][n] = qa[m][n] * ratio;
+          for (int n = 0; n < 5; ++n) {
+            if (qa[n][m] < zero) {
+              qa[n][m] = qa[n][m] * ratio;
+              qa[m][n] = qa[m][n] * ratio;
+            }
           }
         }
       }
@@ -712,19 +841,21 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
         const T d1 = ((one + fallsink1) + qb11) + qb13;
         const T d2 = one + fallsink2;
         const T d3 = one + fallsink3;
-        const T l03 = (-qb03) / d0;
-        const T l13 = (-qb13) / d1;
+        const T r_d0 = CLOUDSC_RCP(d0), r_d1 = CLOUDSC_RCP(d1);
+        (void)r_d0; (void)r_d1;
+        const T l03 = CLOUDSC_DIVR(-qb03, d0, r_d0);
+        const T l13 = CLOUDSC_DIVR(-qb13, d1, r_d1);
         qxn[3] = qxn[3] - l03 * qxn[0];
         qxn[3] = qxn[3] - l13 * qxn[1];
-        qxn[3] = qxn[3] / d3;
-        qxn[2] = qxn[2] / d2;
-        qxn[1] = qxn[1] / d1;
-        qxn[0] = qxn[0] / d0;
+        qxn[3] = CLOUDSC_DIV(qxn[3], d3);
+        qxn[2] = CLOUDSC_DIV(qxn[2], d2);
+        qxn[1] = CLOUDSC_DIVR(qxn[1], d1, r_d1);
+        qxn[0] = CLOUDSC_DIVR(qxn[0], d0, r_d0);
       }
       /* clip small/negative values into vapour, :2402-2412 */
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
-        if (qxn[n] < zepsec) { qxn[4] = qxn[4] + qxn[n]; qxn[n] = zero; }
+        if (qxn[n] < c.zepsec) { qxn[4] = qxn[4] + qxn[n]; qxn[n] = zero; }
       }
       /* variables needed for next level, :2417-2423 */
       s.qlnm1 = qxn[0]; s.qinm1 = qxn[1];
@@ -735,7 +866,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       pf_i_n = (fallsink1 * qxn[1]) * rdtgdp;
       pf_r_n = (fallsink2 * qxn[2]) * rdtgdp;
       pf_s_n = (fallsink3 * qxn[3]) * rdtgdp;
-      if (pf_s_n + pf_r_n < zepsec) s.covptot = zero;
+      if (pf_s_n + pf_r_n < c.zepsec) s.covptot = zero;
 
       /* ================= 6. tendencies, :2456-2506 ======================================== */
       {
@@ -773,7 +904,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
       io.template st<OUT_FHPSL>(k + 1, -c.rlvtt * pfplsl);
       io.template st<OUT_FHPSN>(k + 1, -c.rlstt * pfplsn);
 
-      const T gdph_r = (-zrg_r * (paph_n - s.paph_k)) * zqtmst;
+      const T gdph_r = (sc.neg_zrg_r * (paph_n - s.paph_k)) * zqtmst;
       const T pvfl = io.template ld<IN_PVFL>(k), pvfi = io.template ld<IN_PVFI>(k);
       /* rain/snow rows copy the liquid/ice running sums of the level above (:2550-2555) */
       const T fsqrf = s.fsqlf + (qxn2d[2] - qx0[2]) * gdph_r;
@@ -796,6 +927,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, IO &io, const int klev,
     /* ---- shift the level-(k-1) cache */
     s.tp1_m1 = t; s.a_m1 = a; s.pap_m1 = pap; s.paph_k = paph_n; s.mf_k = mf_n;
     s.pf_i = pf_i_n; s.pf_r = pf_r_n; s.pf_s = pf_s_n;
+    io.level_end(k);
   }
   io.st_rainfrac(s.rainfrac);
 }

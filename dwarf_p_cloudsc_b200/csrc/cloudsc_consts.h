@@ -26,16 +26,64 @@
   X(rdensref) X(rcl_cdenom1) X(rcl_cdenom2) X(rcl_cdenom3) X(rcl_const1r) X(rcl_const2r) \
   X(rcl_const3r) X(rcl_const4r) X(rcl_fac1) X(rcl_fac2) X(rcl_const5r) X(rcl_const6r) X(rcl_fzrab)
 
+/*
+ * Literals of cloudsc_c.c whose binary64 pattern has a non-zero low word.  FP64 instructions can
+ * only encode the high word of an immediate, so such literals would each cost two move
+ * instructions at every use; as members of the constant block they are free `c[bank][offset]`
+ * operands.  (name, value)
+ */
+#define CLOUDSC_DEV_LITERALS(X) \
+  X(zepsec, 1.0e-14) X(one_m_1em6, 1.0 - 1.0e-6) X(p0666, 0.666) X(p1296, 12.96) X(p0639, 0.639) \
+  X(p0024, 0.024) X(p221, 2.21) X(p78, 7.8) X(p887, 8.87) X(p08, 0.8) X(p02, 0.2) X(p099, 0.99) \
+  X(p001, 0.01) X(p03, 0.3) X(p04, 0.4) X(p05777, 0.5777) X(p078, 0.78) X(ztw1, 1329.31) \
+  X(ztw2, 0.0074615) X(ztw4, 40.637)
+
 template <typename T>
 struct CloudscConst {
 #define CLOUDSC_X(n) T n;
   CLOUDSC_DEV_CST(CLOUDSC_X)
   CLOUDSC_DEV_CLDP(CLOUDSC_X)
 #undef CLOUDSC_X
+#define CLOUDSC_X(n, v) T n;
+  CLOUDSC_DEV_LITERALS(CLOUDSC_X)
+#undef CLOUDSC_X
+  T zepsilon;                           /* 100*epsilon(T), cloudsc_c.c:360 */
   /* pow(rcl_kk_cloud_num_{sea,land}, rcl_kkbaun): per-run constants of cloudsc_c.c:1721 */
   T kk_num_pow_sea, kk_num_pow_land;
+  /* reciprocals of run constants (used by the fast-arithmetic build only) */
+  T r_rd, r_rv, r_rtaumel, r_rlcritsnow, r_rdepliqrefdepth, r_rvrfactor, r_15000, r_273, r_p02, r_p0024;
   int nssopt;
   int ncldtop;
+};
+
+/*
+ * Per-launch constants: everything cloudsc_c.c derives from PTSPHY and the parameter objects before
+ * its loops (:385-391 and the loop-invariant sub-expressions it re-evaluates per point).  Passed to
+ * the kernel BY VALUE, i.e. it lives in the kernel-parameter constant bank.  Each member is exactly
+ * the sub-expression the reference evaluates (same operands, same association), so precomputing it
+ * on the host does not change a single bit of the result.
+ */
+template <typename T>
+struct StepConst {
+  T ptsphy;
+  T zqtmst;        /* 1/ptsphy                    :385 */
+  T zrdcp;         /* rd/rcpd                     :387 */
+  T zrdcp_half;    /* zrdcp*0.5                   :1025 */
+  T zrg_r;         /* 1/rg                        :390 */
+  T neg_zrg_r;     /* -zrg_r                      :2547 */
+  T zrldcp;        /* 1/(ralsdcp-ralvdcp)         :391 */
+  T r_ptsphy_rg;   /* 1/(ptsphy*rg)               :807 */
+  T half_rg;       /* 0.5*rg                      :1146 */
+  T ldifdt;        /* rcldiff*ptsphy              :1088 */
+  T ldifdt_conv;   /* rcldiff_convi*ldifdt        :1091 */
+  T faci_koop;     /* ptsphy/rkooptau             :889 */
+  T snowlin;       /* ptsphy*rsnowlin1            :1624 */
+  T rv_rd;         /* rv/rd                       :2011 */
+  T rg_rpecons;    /* rg*rpecons                  :2065 */
+  T one_m_ramin;   /* 1-ramin                     :898 */
+  T one_m_zepsec;  /* 1-zepsec                    :1254 */
+  T one_m_ramid;   /* 1-ramid                     :1263 */
+  T one_m_rprecrhmax; /* 1-rprecrhmax             :1990 */
 };
 
 #endif

@@ -38,10 +38,49 @@ static inline void fill_consts(const struct TECLDP *p, const struct cloudsc_cons
 #define CLOUDSC_X(n) out->n = (T)p->n;
   CLOUDSC_DEV_CLDP(CLOUDSC_X)
 #undef CLOUDSC_X
+#define CLOUDSC_X(n, v) out->n = (T)(v);
+  CLOUDSC_DEV_LITERALS(CLOUDSC_X)
+#undef CLOUDSC_X
+  out->zepsilon = (T)100.0 * (sizeof(T) == 8 ? (T)2.220446049250313e-16 : (T)1.1920929e-07f);
+  out->r_rd = (T)(1.0 / k->rd);
+  out->r_rv = (T)(1.0 / k->rv);
+  out->r_rtaumel = (T)(1.0 / p->rtaumel);
+  out->r_rlcritsnow = (T)(1.0 / p->rlcritsnow);
+  out->r_rdepliqrefdepth = (T)(1.0 / p->rdepliqrefdepth);
+  out->r_rvrfactor = (T)(1.0 / p->rvrfactor);
+  out->r_15000 = (T)(1.0 / 15000.0);
+  out->r_273 = (T)(1.0 / 273.0);
+  out->r_p02 = (T)(1.0 / 0.2);
+  out->r_p0024 = (T)(1.0 / 0.024);
   out->kk_num_pow_sea = (T)std::pow(p->rcl_kk_cloud_num_sea, p->rcl_kkbaun);
   out->kk_num_pow_land = (T)std::pow(p->rcl_kk_cloud_num_land, p->rcl_kkbaun);
   out->nssopt = p->nssopt;
   out->ncldtop = p->ncldtop;
+}
+
+/* Per-launch constants; every member is computed in T with the reference's own expression. */
+template <typename T>
+static inline void fill_step(const CloudscConst<T> &c, double ptsphy_d, StepConst<T> *s) {
+  const T one = (T)1.0, ptsphy = (T)ptsphy_d;
+  s->ptsphy = ptsphy;
+  s->zqtmst = one / ptsphy;
+  s->zrdcp = c.rd / c.rcpd;
+  s->zrdcp_half = s->zrdcp * (T)0.5;
+  s->zrg_r = one / c.rg;
+  s->neg_zrg_r = -s->zrg_r;
+  s->zrldcp = one / (c.ralsdcp - c.ralvdcp);
+  s->r_ptsphy_rg = one / (ptsphy * c.rg);
+  s->half_rg = (T)0.5 * c.rg;
+  s->ldifdt = c.rcldiff * ptsphy;
+  s->ldifdt_conv = c.rcldiff_convi * s->ldifdt;
+  s->faci_koop = ptsphy / c.rkooptau;
+  s->snowlin = ptsphy * c.rsnowlin1;
+  s->rv_rd = c.rv / c.rd;
+  s->rg_rpecons = c.rg * c.rpecons;
+  s->one_m_ramin = one - c.ramin;
+  s->one_m_zepsec = one - c.zepsec;
+  s->one_m_ramid = one - c.ramid;
+  s->one_m_rprecrhmax = one - c.rprecrhmax;
 }
 
 } /* namespace cloudsc */

@@ -9,6 +9,7 @@
  */
 #include "cloudsc_kernels.cuh"
 #include "cloudsc_column.cuh"
+#include "cloudsc_fill.h"
 
 namespace cloudsc {
 
@@ -81,11 +82,13 @@ struct GlobalIO {
   __device__ __forceinline__ T plsm() const { return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PLSM]) + off1); }
   __device__ __forceinline__ int ktype() const { return __ldg(static_cast<const int *>(ft.p[CLOUDSC_F_KTYPE]) + off1); }
   __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
+  __device__ __forceinline__ void level_begin(int) {}
+  __device__ __forceinline__ void level_end(int) {}
 };
 
 template <typename T, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-cloudsc_sweep_direct(const __grid_constant__ FieldTable ft, const LaunchGeom g, const T ptsphy) {
+cloudsc_sweep_direct(const __grid_constant__ FieldTable ft, const LaunchGeom g, const __grid_constant__ StepConst<T> sc) {
   const int col = g.col_begin + blockIdx.x * BLOCK + threadIdx.x;
   if (col >= g.col_end) return;
   const int ibl = col / g.nproma;
@@ -96,41 +99,86 @@ cloudsc_sweep_direct(const __grid_constant__ FieldTable ft, const LaunchGeom g, 
                  (long long)ibl * 5 * g.klev * g.nproma + jl,
                  (long long)ibl * g.nproma + jl,
                  g.nproma, g.klev};
-  cloudsc_column<T>(dev_consts<T>(), io, g.klev, ptsphy);
+  cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
 }
 
 /* ---- host side -------------------------------------------------------------------------------- */
+/* host mirrors of the constant blocks of the current device (per-launch constants derive from them) */
+static CloudscConst<double> h_const64[64];
+static CloudscConst<float> h_const32[64];
+template <typename T> static const CloudscConst<T> &host_consts(int dev);
+template <> const CloudscConst<double> &host_consts<double>(int dev) { return h_const64[dev & 63]; }
+template <> const CloudscConst<float> &host_consts<float>(int dev) { return h_const32[dev & 63]; }
+
 cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<float> &c32) {
-  cudaError_t e = cudaMemcpyToSymbol(g_const64, &c64, sizeof(c64));
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  return cudaMemcpyToSymbol(g_const32, &c32, sizeof(c32));
+  e = cudaMemcpyToSymbol(g_const64, &c64, sizeof(c64));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(g_const32, &c32, sizeof(c32));
+  if (e != cudaSuccess) return e;
+  h_const64[dev & 63] = c64;
+  h_const32[dev & 63] = c32;
+  return cudaSuccess;
 }
 
 namespace {
 constexpr int kDirectBlock = 128;
 
-template <typename T>
-cudaError_t launch_direct(const FieldTable &ft, const LaunchGeom &g, double ptsphy, cudaStream_t stream) {
+/* register budget of the direct kernel = 65536 / (128 * MINB): 2 -> 255, 3 -> 168, 4 -> 128 */
+inline int direct_minb(int variant) {
+  switch (variant) {
+    case VARIANT_DIRECT_R255: return 2;
+    case VARIANT_DIRECT_R128: return 4;
+    case VARIANT_DIRECT_R168:
+    default: return 3;
+  }
+}
+
+template <typename T, int MINB>
+cudaError_t launch_direct_mb(const FieldTable &ft, const LaunchGeom &g, double ptsphy, cudaStream_t stream) {
   const int ncols = g.col_end - g.col_begin;
   const int grid = (ncols + kDirectBlock - 1) / kDirectBlock;
-  cloudsc_sweep_direct<T, kDirectBlock, 1><<<grid, kDirectBlock, 0, stream>>>(ft, g, (T)ptsphy);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  StepConst<T> sc;
+  fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
+  cloudsc_sweep_direct<T, kDirectBlock, MINB><<<grid, kDirectBlock, 0, stream>>>(ft, g, sc);
   return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_direct(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int variant, cudaStream_t stream) {
+  switch (direct_minb(variant)) {
+    case 2: return launch_direct_mb<T, 2>(ft, g, ptsphy, stream);
+    case 4: return launch_direct_mb<T, 4>(ft, g, ptsphy, stream);
+    default: return launch_direct_mb<T, 3>(ft, g, ptsphy, stream);
+  }
+}
+
+template <typename T>
+const void *direct_fn(int variant) {
+  switch (direct_minb(variant)) {
+    case 2: return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 2>;
+    case 4: return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 4>;
+    default: return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 3>;
+  }
 }
 }  // namespace
 
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,
                          cudaStream_t stream) {
   if (g.col_end <= g.col_begin) return cudaSuccess;
-  (void)variant;
-  if (precision == CLOUDSC_B200_FP32) return launch_direct<float>(ft, g, ptsphy, stream);
-  return launch_direct<double>(ft, g, ptsphy, stream);
+  if (precision == CLOUDSC_B200_FP32) return launch_direct<float>(ft, g, ptsphy, variant, stream);
+  return launch_direct<double>(ft, g, ptsphy, variant, stream);
 }
 
 cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]) {
-  (void)nproma; (void)variant;
+  (void)nproma;
   cudaFuncAttributes a;
-  const void *fn = precision == CLOUDSC_B200_FP32 ? (const void *)cloudsc_sweep_direct<float, kDirectBlock, 1>
-                                                  : (const void *)cloudsc_sweep_direct<double, kDirectBlock, 1>;
+  const void *fn = precision == CLOUDSC_B200_FP32 ? direct_fn<float>(variant) : direct_fn<double>(variant);
   cudaError_t e = cudaFuncGetAttributes(&a, fn);
   if (e != cudaSuccess) return e;
   int nb = 0;
@@ -142,7 +190,7 @@ cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]
   out[3] = a.maxThreadsPerBlock;
   out[4] = nb;
   out[5] = kDirectBlock;
-  out[6] = VARIANT_DIRECT;
+  out[6] = variant;
   out[7] = 0;
   return cudaSuccess;
 }

@@ -26,8 +26,10 @@ struct LaunchGeom {
 
 enum Variant {
   VARIANT_AUTO = 0,
-  VARIANT_DIRECT = 1,   /* one thread per column, loads/stores straight from/to global memory */
-  VARIANT_STAGED = 2,   /* warp-private TMA (cp.async.bulk) + mbarrier staging of the level tiles */
+  /* one thread per column, loads/stores straight from/to global memory; three register budgets */
+  VARIANT_DIRECT_R255 = 1,  /* 2 CTAs of 128 threads per SM */
+  VARIANT_DIRECT_R168 = 2,  /* 3 CTAs per SM */
+  VARIANT_DIRECT_R128 = 3,  /* 4 CTAs per SM */
   VARIANT_COUNT
 };
 

@@ -3,7 +3,9 @@
  *
  * Compiles the exact header the CUDA kernels instantiate, for the host, with FP contraction off,
  * so that `-m "not gpu"` tests can check the re-organised (k-cached, sparse-solve) arithmetic
- * bit-for-bit against the reference kernel without a GPU.  Never linked into, loaded by, or
+ * without a GPU.  Built twice by oracle/Makefile: -DCLOUDSC_STRICT=1 (libcloudsc_emul.so, must be
+ * bit-identical to the reference kernel) and -DCLOUDSC_STRICT=0 (libcloudsc_emul_fast.so, the
+ * arithmetic mode of the product kernels: shared reciprocals, polynomial exp).  Never linked into, loaded by, or
  * reachable from the product library: libcloudsc_b200.so has no host arithmetic path.
  */
 #include <cstddef>
@@ -48,6 +50,8 @@ struct HostIO {
   T plsm() const { return ((const T *)f[CLOUDSC_F_PLSM])[jl]; }
   int ktype() const { return ((const int *)f[CLOUDSC_F_KTYPE])[jl]; }
   void st_rainfrac(T v) { ((T *)f[CLOUDSC_F_PRAINFRAC_TOPRFZ])[jl] = v; }
+  void level_begin(int) {}
+  void level_end(int) {}
 };
 
 template <typename T>
@@ -56,6 +60,8 @@ int run(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fiel
   if (check_params(p)) return CLOUDSC_B200_EPARAMS;
   CloudscConst<T> c;
   fill_consts<T>(p, k, &c);
+  StepConst<T> sc;
+  fill_step<T>(c, ptsphy, &sc);
   const int nblocks = (ngptot + nproma - 1) / nproma;
 #pragma omp parallel for schedule(static)
   for (int b = 0; b < nblocks; b++) {
@@ -68,7 +74,7 @@ int run(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fiel
     const int bsize = (ngptot - b * nproma) < nproma ? (ngptot - b * nproma) : nproma;
     for (int jl = 0; jl < bsize; jl++) {
       HostIO<T> io{pb, jl, nproma, klev};
-      cloudsc_column<T>(c, io, klev, (T)ptsphy);
+      cloudsc_column<T>(c, sc, io, klev);
     }
   }
   return 0;

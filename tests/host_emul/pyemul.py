@@ -8,8 +8,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 class Emul:
-    def __init__(self):
-        self.lib = ctypes.CDLL(os.path.join(HERE, "libcloudsc_emul.so"), mode=ctypes.RTLD_LOCAL)
+    def __init__(self, fast=False):
+        """fast=False: CLOUDSC_STRICT=1 build (reference evaluation order); fast=True: the product
+        kernels' arithmetic mode (shared reciprocals, polynomial exp)."""
+        name = "libcloudsc_emul_fast.so" if fast else "libcloudsc_emul.so"
+        self.lib = ctypes.CDLL(os.path.join(HERE, name), mode=ctypes.RTLD_LOCAL)
         for n in ("cloudsc_emul_blocks_f64", "cloudsc_emul_blocks_f32"):
             fn = getattr(self.lib, n)
             fn.restype = ctypes.c_int
