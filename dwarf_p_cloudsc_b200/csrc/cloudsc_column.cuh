@@ -225,8 +225,14 @@ CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
 
 /*
  * The column sweep.  IO must provide
- *   template<int S> T ld(int k) const;        input slot S at level k (0-based; IN_PAPH: row k)
- *   template<int S> void st(int k, T v);      output slot S at row k
+ *   template<int S> T ld(int k) const;        input slot S at level k (0-based), read while level k
+ *                                             is being processed
+ *   template<int S> T ld_next(int k) const;   row k+1 of slot S, read while level k is processed
+ *                                             (IN_PAPH, IN_PMFU, IN_PMFD, IN_PLU only)
+ *   T paph_row(int r) const;                  paph row r outside the level loop (r = 0, klev)
+ *   template<int S> void st(int k, T v);      output slot S: row k (tendencies, pcovptot, plude) or
+ *                                             row k+1 passed as k+1 (flux fields), once per level
+ *   template<int S> void st_row0(T v);        row 0 of a flux field (before the level loop)
  *   T plsm() const; int ktype() const; void st_rainfrac(T);
  *   void level_begin(int k); void level_end(int k);   hooks for staged IO (may be empty)
  */
@@ -241,7 +247,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   const int ktop = c.ncldtop - 1; /* first level (0-based) of the physics sweep, :732 */
 
   /* per-column constants */
-  const T paph_surf = io.template ld<IN_PAPH>(klev); /* paph[klev+1] :1260,2064 */
+  const T paph_surf = io.paph_row(klev); /* paph[klev+1] :1260,2064 */
   const T r_paph_surf = CLOUDSC_RCP(paph_surf);
   (void)r_paph_surf;
   const T plsm = io.plsm();
@@ -253,7 +259,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 
   Carry<T> s;
   s.tp1_m1 = zero; s.a_m1 = zero; s.pap_m1 = zero;
-  s.paph_k = io.template ld<IN_PAPH>(0);
+  s.paph_k = io.paph_row(0);
   s.mf_k = zero;
   s.anewm1 = zero; s.qlnm1 = zero; s.qinm1 = zero;           /* :718 */
   s.pf_i = zero; s.pf_r = zero; s.pf_s = zero;               /* :493 */
@@ -262,19 +268,19 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   s.fsqlf = zero; s.fsqif = zero; s.fcqlng = zero; s.fcqnng = zero; s.fsqltur = zero; s.fsqitur = zero;
 
   /* row 0 of every flux output, :2533-2542 and zpfplsx[.][0]=0 -> :2523-2524,2578-2579 */
-  io.template st<OUT_FSQLF>(0, zero);  io.template st<OUT_FSQIF>(0, zero);
-  io.template st<OUT_FSQRF>(0, zero);  io.template st<OUT_FSQSF>(0, zero);
-  io.template st<OUT_FCQLNG>(0, zero); io.template st<OUT_FCQNNG>(0, zero);
-  io.template st<OUT_FCQRNG>(0, zero); io.template st<OUT_FCQSNG>(0, zero);
-  io.template st<OUT_FSQLTUR>(0, zero); io.template st<OUT_FSQITUR>(0, zero);
-  io.template st<OUT_FPLSL>(0, zero);  io.template st<OUT_FPLSN>(0, zero);
-  io.template st<OUT_FHPSL>(0, -c.rlvtt * zero); io.template st<OUT_FHPSN>(0, -c.rlstt * zero);
+  io.template st_row0<OUT_FSQLF>(zero);  io.template st_row0<OUT_FSQIF>(zero);
+  io.template st_row0<OUT_FSQRF>(zero);  io.template st_row0<OUT_FSQSF>(zero);
+  io.template st_row0<OUT_FCQLNG>(zero); io.template st_row0<OUT_FCQNNG>(zero);
+  io.template st_row0<OUT_FCQRNG>(zero); io.template st_row0<OUT_FCQSNG>(zero);
+  io.template st_row0<OUT_FSQLTUR>(zero); io.template st_row0<OUT_FSQITUR>(zero);
+  io.template st_row0<OUT_FPLSL>(zero);  io.template st_row0<OUT_FPLSN>(zero);
+  io.template st_row0<OUT_FHPSL>(-c.rlvtt * zero); io.template st_row0<OUT_FHPSN>(-c.rlstt * zero);
 
   for (int k = 0; k < klev; ++k) {
     io.level_begin(k);
     /* ================= 1. initial values of this level, :462-485 ========================== */
     const T pap = io.template ld<IN_PAP>(k);
-    const T paph_n = io.template ld<IN_PAPH>(k + 1);
+    const T paph_n = io.template ld_next<IN_PAPH>(k);
     const T t = io.template ld<IN_PT>(k) + ptsphy * io.template ld<IN_TT>(k);
     T qv = io.template ld<IN_PQ>(k) + ptsphy * io.template ld<IN_TQ>(k);
     T a = io.template ld<IN_PA>(k) + ptsphy * io.template ld<IN_TA>(k);
@@ -328,7 +334,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
     T tend_a = zero, tcld[4] = {zero, zero, zero, zero}, covptot_out = zero;
     T pf_i_n = zero, pf_r_n = zero, pf_s_n = zero;  /* zpfplsx[.][jk+1] */
     /* pmfu+pmfd of the level below (:1067,1143); becomes mf_k of the next iteration (needs ncldtop >= 2) */
-    const T mf_n = (k + 1 < klev && k + 1 >= ktop) ? io.template ld<IN_PMFU>(k + 1) + io.template ld<IN_PMFD>(k + 1) : zero;
+    const T mf_n = (k + 1 < klev && k + 1 >= ktop) ? io.template ld_next<IN_PMFU>(k) + io.template ld_next<IN_PMFD>(k) : zero;
 
     if (k >= ktop) {
       /* ================= saturation values of this level, :583-640 ======================== */
@@ -438,7 +444,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 
       /* ================= 3.2 detrainment from convection, :967-987 ======================== */
       if (k + 1 < klev) {
-        const T plu_n = io.template ld<IN_PLU>(k + 1);
+        const T plu_n = io.template ld_next<IN_PLU>(k);
         plude_out = plude_out * dtgdp;
         if (plu_n > c.zepsec && plude_out > c.rlmin) {
           solac = solac + CLOUDSC_DIV(plude_out, plu_n);
@@ -450,7 +456,6 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           plude_out = zero;
         }
         qa[3][3] = qa[3][3] + io.template ld<IN_PSNDE>(k) * dtgdp;
-        io.template st<OUT_PLUDE>(k, plude_out);
       }
 
       /* ================= 3.3 subsidence compensating convective updraughts, :1002-1075 ==== */
@@ -894,6 +899,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
     io.template st<OUT_TCLD2>(k, tcld[2]); io.template st<OUT_TCLD3>(k, tcld[3]);
     io.template st<OUT_TCLD4>(k, zero);    /* cloudsc_driver.c:200 */
     io.template st<OUT_COVPTOT>(k, covptot_out); /* :2505; zero above ncldtop per cloudsc_driver.c:199 */
+    io.template st<OUT_PLUDE>(k, plude_out);     /* in/out: the loaded value where :970-980 does not apply */
 
     /* ================= 8. flux diagnostics for row k+1, :2521-2582 ========================= */
     {

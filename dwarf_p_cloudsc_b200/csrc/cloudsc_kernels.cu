@@ -11,6 +11,8 @@
 #include "cloudsc_column.cuh"
 #include "cloudsc_fill.h"
 
+#include <cstdint>
+
 namespace cloudsc {
 
 __constant__ CloudscConst<double> g_const64;
@@ -73,6 +75,8 @@ struct GlobalIO {
     if (S == IN_PLUDE) return base[off];
     return __ldg(base + off);
   }
+  template <int S> __device__ __forceinline__ T ld_next(int k) const { return ld<S>(k + 1); }
+  __device__ __forceinline__ T paph_row(int r) const { return ld<IN_PAPH>(r); }
   template <int S> __device__ __forceinline__ void st(int k, T v) {
     T *base = static_cast<T *>(ft.p[out_field(S)]);
     const long long off = (out_kind(S) == 0 ? offL : out_kind(S) == 1 ? offH : offC + (long long)out_species(S) * klev * stride)
@@ -82,6 +86,7 @@ struct GlobalIO {
   __device__ __forceinline__ T plsm() const { return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PLSM]) + off1); }
   __device__ __forceinline__ int ktype() const { return __ldg(static_cast<const int *>(ft.p[CLOUDSC_F_KTYPE]) + off1); }
   __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
+  template <int S> __device__ __forceinline__ void st_row0(T v) { st<S>(0, v); }
   __device__ __forceinline__ void level_begin(int) {}
   __device__ __forceinline__ void level_end(int) {}
 };
@@ -99,6 +104,155 @@ cloudsc_sweep_direct(const __grid_constant__ FieldTable ft, const LaunchGeom g, 
                  (long long)ibl * 5 * g.klev * g.nproma + jl,
                  (long long)ibl * g.nproma + jl,
                  g.nproma, g.klev};
+  cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+}
+
+/* ---- IO policy 2: TMA-staged input tiles shared by the CTA, streaming stores ------------------- */
+/*
+ * A CTA of WARPS warps owns 32*WARPS consecutive columns of ONE NPROMA block, so one (field, level)
+ * row of the CTA is 32*WARPS*sizeof(T) contiguous, 16-byte aligned bytes: exactly one
+ * `cp.async.bulk` (TMA; SASS UBLKCP).
+ *
+ * INPUTS.  Per level the column code needs N_IN = 27 rows.  They are fetched TWO LEVELS AHEAD into
+ * a 2-stage shared-memory ring, signalled through one "full" mbarrier per stage:
+ *   level_begin(k): every thread waits on the phase of full[k&1];
+ *   ld<S>(k):       ONE LDS at [stage + S*row + tid] -- no global address arithmetic in the consumer;
+ *   level_end(k):   lane 0 of every warp arrives on empty[k&1]; thread 0 waits until all WARPS warps
+ *                   have arrived (the stage is no longer read), arms full[k&1] with expect_tx and
+ *                   issues the 27 bulk copies of level k+2.  All of thread 0's operands derive from
+ *                   blockIdx / kernel parameters, so the copy loop runs on the uniform datapath.
+ * Rows of the fields read at level k+1 while level k is processed (paph, pmfu, pmfd, plu) are stored
+ * in the stage of level k, so a stage holds exactly what one iteration consumes.  A whole level of
+ * compute (~10 us per warp) lies between issue and use: the long-scoreboard stalls of the direct
+ * kernel disappear without spending registers on prefetch.
+ *
+ * OUTPUTS go straight from registers to global memory as streaming stores (st.global.cs); stores do
+ * not stall the issuing warp, and keeping them out of shared memory leaves room for 12-16 resident
+ * warps per SM (2 stages x 27 rows x 1 KB = 54 KB per 4-warp CTA).
+ */
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+/* 1 for the input slots whose row k+1 is staged with level k */
+__host__ __device__ constexpr int in_next(int s) { return (s == IN_PAPH || s == IN_PMFU || s == IN_PMFD || s == IN_PLU) ? 1 : 0; }
+
+template <typename T, int WARPS>
+struct TileIO {
+  static constexpr int kCols = 32 * WARPS;                 /* columns of the CTA tile */
+  static constexpr int kRow = kCols * (int)sizeof(T);      /* bytes of one staged row */
+  static constexpr int kStage = N_IN * kRow;               /* one input stage */
+  static constexpr int kSmem = 2 * kStage + 32;            /* + full[2], empty[2] mbarriers */
+  const FieldTable &ft;
+  /* CTA-uniform: element offsets of (block, level 0, first column of the tile) per field kind */
+  long long tileL, tileH, tileC;
+  int stride, klev;                   /* nproma, klev */
+  unsigned smem0;                     /* shared address of stage 0 */
+  unsigned bar0;                      /* shared address of full[0]; full[1] +8, empty[0] +16, empty[1] +24 */
+  /* per thread */
+  const T *stage_t;                   /* generic pointer: stage 0 + tid */
+  const T *cur;                       /* stage of the level being processed + tid */
+  long long offL, offH, offC, off1;   /* element offsets of this thread's column (stores, scalars) */
+
+  __device__ __forceinline__ void issue(int level) {   /* thread 0 only */
+    const unsigned st = (unsigned)level & 1u;
+    const unsigned bar = bar0 + 8u * st;
+    const unsigned dst = smem0 + st * (unsigned)kStage;
+    mbar_arrive_expect_tx(bar, (unsigned)kStage);
+    const long long r0 = (long long)level * stride;
+    /* pmfu/pmfd/plu have klev rows: at the last level their "next" row does not exist and is not
+       read; re-fetch the last row to keep the transaction count of the stage constant */
+    const long long r1 = (long long)(level + 1 < klev ? level + 1 : klev - 1) * stride;
+    const long long r1h = (long long)(level + 1) * stride;
+#pragma unroll
+    for (int s = 0; s < N_IN; ++s) {
+      const long long tile = in_kind(s) == 0 ? tileL : in_kind(s) == 1 ? tileH : tileC + (long long)in_species(s) * klev * stride;
+      const long long row = s == IN_PAPH ? r1h : in_next(s) ? r1 : r0;
+      bulk_g2s(dst + (unsigned)(s * kRow), static_cast<const T *>(ft.p[in_field(s)]) + (tile + row), (unsigned)kRow, bar);
+    }
+  }
+  __device__ __forceinline__ void level_begin(int k) {
+    cur = stage_t + (k & 1) * (kStage / (int)sizeof(T));
+    mbar_wait(bar0 + 8u * ((unsigned)k & 1u), ((unsigned)k >> 1) & 1u);
+  }
+  __device__ __forceinline__ void level_end(int k) {
+    __syncwarp();               /* every lane of this warp is done reading stage k&1 */
+    if (WARPS > 1 && (threadIdx.x & 31) == 0) mbar_arrive(bar0 + 16u + 8u * ((unsigned)k & 1u));
+    if (threadIdx.x == 0 && k + 2 < klev) {
+      if (WARPS > 1) mbar_wait(bar0 + 16u + 8u * ((unsigned)k & 1u), ((unsigned)k >> 1) & 1u);
+      issue(k + 2);
+    }
+  }
+  template <int S> __device__ __forceinline__ T ld(int) const { return cur[S * kCols]; }
+  template <int S> __device__ __forceinline__ T ld_next(int) const { return cur[S * kCols]; }
+  __device__ __forceinline__ T paph_row(int r) const {
+    return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PAPH]) + offH + (long long)r * stride);
+  }
+  template <int S> __device__ __forceinline__ void st(int k, T v) {
+    T *base = static_cast<T *>(ft.p[out_field(S)]);
+    const long long off = (out_kind(S) == 0 ? offL : out_kind(S) == 1 ? offH : offC + (long long)out_species(S) * klev * stride)
+                        + (long long)k * stride;
+    __stcs(base + off, v);
+  }
+  template <int S> __device__ __forceinline__ void st_row0(T v) { st<S>(0, v); }
+  __device__ __forceinline__ T plsm() const { return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PLSM]) + off1); }
+  __device__ __forceinline__ int ktype() const { return __ldg(static_cast<const int *>(ft.p[CLOUDSC_F_KTYPE]) + off1); }
+  __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
+};
+
+template <typename T, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+cloudsc_sweep_tile(const __grid_constant__ FieldTable ft, const LaunchGeom g, const __grid_constant__ StepConst<T> sc) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using IO = TileIO<T, WARPS>;
+  /* first column of this CTA; col_begin, col_end and nproma are multiples of 32*WARPS (launcher) */
+  const int ccol = g.col_begin + blockIdx.x * IO::kCols;
+  if (ccol >= g.col_end) return;  /* CTA-uniform */
+  const int ibl = ccol / g.nproma;
+  const int jl0 = ccol - ibl * g.nproma;
+  const int jl = jl0 + (int)threadIdx.x;
+  const long long bL = (long long)ibl * g.klev * g.nproma, bH = (long long)ibl * (g.klev + 1) * g.nproma;
+
+  IO io{ft, bL + jl0, bH + jl0, bL * 5 + jl0, g.nproma, g.klev,
+        smem_u32(smem_raw), smem_u32(smem_raw + 2 * IO::kStage),
+        reinterpret_cast<const T *>(smem_raw) + threadIdx.x,
+        nullptr, bL + jl, bH + jl, bL * 5 + jl, (long long)ibl * g.nproma + jl};
+  if (threadIdx.x == 0) {
+    mbar_init(io.bar0, 1);
+    mbar_init(io.bar0 + 8, 1);
+    mbar_init(io.bar0 + 16, WARPS);
+    mbar_init(io.bar0 + 24, WARPS);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    io.issue(0);
+    if (g.klev > 1) io.issue(1);
+  }
   cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
 }
 
@@ -166,32 +320,135 @@ const void *direct_fn(int variant) {
     default: return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 3>;
   }
 }
+
+/* ---- tile (TMA-staged) variant ------------------------------------------------------------------ */
+/* (warps per CTA, resident warps per SM the register budget is sized for: 8 -> 255 regs, 12 -> 168, 16 -> 128) */
+struct TileCfg { int warps, wps; };
+inline bool is_tile(int variant) { return variant == VARIANT_AUTO || (variant >= VARIANT_TILE_C4_W8 && variant <= VARIANT_TILE_C2_W12); }
+/* widest CTA tile whose 32*WARPS columns never straddle an NPROMA block */
+inline int tile_warps_for(int nproma) { return nproma % 128 == 0 ? 4 : nproma % 64 == 0 ? 2 : nproma % 32 == 0 ? 1 : 0; }
+inline TileCfg tile_cfg(int variant, int nproma) {
+  const int widest = tile_warps_for(nproma);
+  /* default: one-warp CTAs (warp-private tiles, no coupling between warps), 12 resident warps per SM
+     -- the fastest configuration measured on B200 (profiles/README.md) */
+  TileCfg c = {widest ? 1 : 0, 12};
+  switch (variant) {
+    case VARIANT_TILE_C4_W8: c.warps = widest; c.wps = 8; break;
+    case VARIANT_TILE_C4_W12: c.warps = widest; break;
+    case VARIANT_TILE_C4_W16: c.warps = widest; c.wps = 16; break;
+    case VARIANT_TILE_C2_W12: c.warps = widest >= 2 ? 2 : widest; break;
+    default: break;
+  }
+  if (c.warps != 4) c.wps = 12;   /* the narrow tiles are built for one register budget only */
+  return c;
+}
+
+#define CLOUDSC_TILE_DISPATCH(cfg, ...)                                                   \
+  if (cfg.warps == 4 && cfg.wps == 8) { constexpr int W = 4, MB = 2; __VA_ARGS__; }       \
+  else if (cfg.warps == 4 && cfg.wps == 16) { constexpr int W = 4, MB = 4; __VA_ARGS__; } \
+  else if (cfg.warps == 4) { constexpr int W = 4, MB = 3; __VA_ARGS__; }                  \
+  else if (cfg.warps == 2) { constexpr int W = 2, MB = 6; __VA_ARGS__; }                  \
+  else { constexpr int W = 1, MB = 12; __VA_ARGS__; }
+
+template <typename T>
+const void *tile_fn(TileCfg cfg, size_t *smem) {
+  const void *fn = nullptr;
+  CLOUDSC_TILE_DISPATCH(cfg, (fn = (const void *)cloudsc_sweep_tile<T, W, MB>, *smem = TileIO<T, W>::kSmem))
+  return fn;
+}
+
+/* the TMA rows must be 16-byte aligned and a CTA's columns must not straddle NPROMA blocks */
+template <typename T>
+bool tile_ok(const FieldTable &ft, const LaunchGeom &g, TileCfg cfg) {
+  if (cfg.warps == 0 || g.col_begin % (32 * cfg.warps) != 0) return false;
+  for (int s = 0; s < N_IN; ++s)
+    if (reinterpret_cast<uintptr_t>(ft.p[in_field(s)]) % 16 != 0) return false;
+  return true;
+}
+
+template <typename T>
+cudaError_t launch_tile(const FieldTable &ft, const LaunchGeom &g, double ptsphy, TileCfg cfg, cudaStream_t stream) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  size_t smem = 0;
+  const void *fn = tile_fn<T>(cfg, &smem);
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  const int ncols = g.col_end - g.col_begin;
+  const int per_cta = cfg.warps * 32;
+  const int grid = (ncols + per_cta - 1) / per_cta;
+  StepConst<T> sc;
+  fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
+  void *args[] = {(void *)&ft, (void *)&g, (void *)&sc};
+  return cudaLaunchKernel(fn, dim3(grid), dim3(per_cta), args, smem, stream);
+}
 }  // namespace
+
+template <typename T>
+static cudaError_t launch_any(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int variant, cudaStream_t stream) {
+  const TileCfg cfg = tile_cfg(variant, g.nproma);
+  if (is_tile(variant) && tile_ok<T>(ft, g, cfg)) {
+    /* the TMA kernel moves whole rows of 32*WARPS columns: give it the aligned part of the range and
+       finish a ragged tail with the direct kernel */
+    const int per_cta = 32 * cfg.warps;
+    const int aligned_end = g.col_end - (g.col_end - g.col_begin) % per_cta;
+    cudaError_t e = cudaSuccess;
+    if (aligned_end > g.col_begin) {
+      LaunchGeom ga = g;
+      ga.col_end = aligned_end;
+      e = launch_tile<T>(ft, ga, ptsphy, cfg, stream);
+      if (e != cudaSuccess) return e;
+    }
+    if (aligned_end < g.col_end) {
+      LaunchGeom gt = g;
+      gt.col_begin = aligned_end;
+      e = launch_direct<T>(ft, gt, ptsphy, VARIANT_DIRECT_R168, stream);
+    }
+    return e;
+  }
+  /* geometry the TMA path cannot take (NPROMA not a multiple of 32, unaligned column range or
+     pointers): same arithmetic, plain global loads */
+  return launch_direct<T>(ft, g, ptsphy, is_tile(variant) ? VARIANT_DIRECT_R168 : variant, stream);
+}
 
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,
                          cudaStream_t stream) {
   if (g.col_end <= g.col_begin) return cudaSuccess;
-  if (precision == CLOUDSC_B200_FP32) return launch_direct<float>(ft, g, ptsphy, variant, stream);
-  return launch_direct<double>(ft, g, ptsphy, variant, stream);
+  if (precision == CLOUDSC_B200_FP32) return launch_any<float>(ft, g, ptsphy, variant, stream);
+  return launch_any<double>(ft, g, ptsphy, variant, stream);
 }
 
 cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]) {
-  (void)nproma;
+  const TileCfg cfg = tile_cfg(variant, nproma);
+  const bool tile = is_tile(variant) && cfg.warps > 0;
   cudaFuncAttributes a;
-  const void *fn = precision == CLOUDSC_B200_FP32 ? direct_fn<float>(variant) : direct_fn<double>(variant);
-  cudaError_t e = cudaFuncGetAttributes(&a, fn);
+  size_t dyn = 0;
+  const void *fn = precision == CLOUDSC_B200_FP32 ? (tile ? tile_fn<float>(cfg, &dyn) : direct_fn<float>(variant))
+                                                  : (tile ? tile_fn<double>(cfg, &dyn) : direct_fn<double>(variant));
+  cudaError_t e;
+  if (tile) {
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
+  e = cudaFuncGetAttributes(&a, fn);
   if (e != cudaSuccess) return e;
+  const int threads = tile ? cfg.warps * 32 : kDirectBlock;
   int nb = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kDirectBlock, 0);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, dyn);
   if (e != cudaSuccess) return e;
   out[0] = a.numRegs;
   out[1] = (int)a.localSizeBytes;
   out[2] = (int)a.sharedSizeBytes;
   out[3] = a.maxThreadsPerBlock;
   out[4] = nb;
-  out[5] = kDirectBlock;
+  out[5] = threads;
   out[6] = variant;
-  out[7] = 0;
+  out[7] = (int)dyn;
   return cudaSuccess;
 }
 

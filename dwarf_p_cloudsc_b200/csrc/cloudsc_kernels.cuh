@@ -30,6 +30,14 @@ enum Variant {
   VARIANT_DIRECT_R255 = 1,  /* 2 CTAs of 128 threads per SM */
   VARIANT_DIRECT_R168 = 2,  /* 3 CTAs per SM */
   VARIANT_DIRECT_R128 = 3,  /* 4 CTAs per SM */
+  /* TMA-staged input tiles (cp.async.bulk + mbarrier) of 32*WARPS columns per CTA, streaming stores.
+     Cn = warps per CTA (clamped to what NPROMA allows), Wm = resident-warp target per SM that sets the
+     register budget (8 -> 255, 12 -> 168, 16 -> 128 registers). */
+  VARIANT_TILE_C4_W8 = 4,
+  VARIANT_TILE_C4_W12 = 5,
+  VARIANT_TILE_C4_W16 = 6,
+  VARIANT_TILE_C1_W12 = 7,  /* one-warp CTAs, warp-private tiles; the default (VARIANT_AUTO) */
+  VARIANT_TILE_C2_W12 = 8,
   VARIANT_COUNT
 };
 

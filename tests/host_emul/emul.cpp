@@ -43,10 +43,13 @@ struct HostIO {
     const int sp = (S >= IN_PCLV0 && S <= IN_PCLV3) ? S - IN_PCLV0 : (S >= IN_TCLD0 && S <= IN_TCLD3) ? S - IN_TCLD0 : 0;
     return ((const T *)f[in_field(S)])[(size_t)(sp * klev + k) * stride + jl];
   }
+  template <int S> T ld_next(int k) const { return ld<S>(k + 1); }
+  T paph_row(int r) const { return ld<IN_PAPH>(r); }
   template <int S> void st(int k, T v) {
     const int sp = (S >= OUT_TCLD0 && S <= OUT_TCLD4) ? S - OUT_TCLD0 : 0;
     ((T *)f[out_field(S)])[(size_t)(sp * klev + k) * stride + jl] = v;
   }
+  template <int S> void st_row0(T v) { st<S>(0, v); }
   T plsm() const { return ((const T *)f[CLOUDSC_F_PLSM])[jl]; }
   int ktype() const { return ((const int *)f[CLOUDSC_F_KTYPE])[jl]; }
   void st_rainfrac(T v) { ((T *)f[CLOUDSC_F_PRAINFRAC_TOPRFZ])[jl] = v; }

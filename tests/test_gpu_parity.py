@@ -171,3 +171,23 @@ def test_unsupported_params_fail_loudly(built, input_data):
     with pytest.raises(api.CloudscError) as ei:
         api.set_params(p, k)
     assert ei.value.code == -1 and "laericesed" in str(ei.value)
+
+
+@pytest.mark.parametrize("kernel_variant", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_every_kernel_variant_matches_oracle(built, oracle, input_data, kernel_variant):
+    """All register-budget / IO-policy variants run the same arithmetic: each must meet the parity bar on
+    a ragged geometry (last block partly filled, column count not a multiple of the warp size)."""
+    from dwarf_p_cloudsc_b200 import params, state, api
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    c2 = state.perturb(cols, "warm+land+conv+rain+moist+tend")
+    try:
+        api.set_variant(kernel_variant)
+        for src, (ngptot, nproma) in ((cols, (1000, 128)), (cols, (1221, 64)), (c2, (333, 32))):
+            F = state.blocked_fields(src, ngptot, nproma, klev)
+            R = {n: a.copy() for n, a in F.items()}
+            oracle.run(R, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 0)
+            G = _run_gpu(F, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
+            _compare(G, R, ngptot)
+    finally:
+        api.set_variant(0)

@@ -1,11 +1,11 @@
 #!/bin/bash
-# parity + timing of every kernel variant. usage: bash tools/gpu_variants.sh "1 2 3"
+# parity + timing of every kernel variant. usage: bash tools/gpu_variants.sh "1 2 3" [pytest -k expr]
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout -s KILL 1500 python -m pytest tests -m gpu -x -q ${2:+-k "$2"} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
 for v in ${1:-1 2 3}; do
-  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --variant $v > gpurun_out/bench_v$v.json 2> gpurun_out/bench_v$v.err
+  timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --variant $v > gpurun_out/bench_v$v.json 2> gpurun_out/bench_v$v.err
   python - <<PY
 import json
 try:
