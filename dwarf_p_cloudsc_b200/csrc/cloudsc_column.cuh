@@ -145,32 +145,104 @@ CLOUDSC_FN double exp_fast(double x) {
 }
 CLOUDSC_FN float exp_fast(float x) { return ex_lib(x); }
 
-/* 1/x by the hardware seed + two Newton steps, no zero/inf/denormal path (every divisor of the
+/* 1/x by the hardware seed (MUFU.RCP64H, ~2^-20) + one cubically convergent step
+ * r(1 + e + e^2), e = 1 - x r  (error e^3 ~ 2^-60), no zero/inf/denormal path (every divisor of the
  * scheme is a normal number bounded away from 0 by an explicit max(., eps) or by its physics). */
 CLOUDSC_FN double rcp_fast(double x) {
 #if defined(__CUDACC__)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  const double e = fma(-x, r, 1.0);
+  const double p = fma(e, e, e);
+  return fma(r, p, r);
 #else
   return 1.0 / x;
 #endif
 }
 CLOUDSC_FN float rcp_fast(float x) { return 1.0f / x; }
 
+/*
+ * log(x) for normal positive x: x = m 2^e with m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1),
+ * log m = 2 atanh s = 2s + 2 s z g(z), z = s^2, g a degree-6 polynomial (tools/fit_log.py, fit error
+ * 4e-18 relative to log m).  ~35 instructions.  x = 0 / denormal return about -709 (callers only use it
+ * under exp_fast(y * log x), where that underflows to ~0 like the exact result).
+ */
+CLOUDSC_FN double log_fast(double x) {
+#if defined(__CUDACC__)
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+#else
+  long long xb;
+  std::memcpy(&xb, &x, 8);
+  int hi = (int)(xb >> 32);
+  const int lo = (int)(xb & 0xffffffffLL);
+#endif
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }
+#if defined(__CUDACC__)
+  const double m = __hiloint2double(hi, lo);
+#else
+  double m;
+  xb = ((long long)hi << 32) | (long long)(unsigned)lo;
+  std::memcpy(&m, &xb, 8);
+#endif
+  const double s = (m - 1.0) * rcp_fast(m + 1.0);
+  const double z = s * s;
+  double g = 0.07308292712444311;
+  g = g * z + 0.07665855309105386;
+  g = g * z + 0.09091444727837474;
+  g = g * z + 0.11111105565129939;
+  g = g * z + 0.14285714313001635;
+  g = g * z + 0.19999999999949722;
+  g = g * z + 0.3333333333333335;
+  const double lm = (s * z) * g + s;           /* atanh s */
+  const double fe = (double)e;
+  return fe * 6.93147180369123816490e-01 + (fe * 1.90821492927058770002e-10 + (lm + lm));
+}
+/* x^y for x > 0 as exp(y log x): relative error ~ |y log x| * 2e-16 (library pow: 0.5 ulp at ~15x the
+ * instructions and a call into a spilling slow path).  exp_fast is declared above. */
+CLOUDSC_FN double pow_fast(double x, double y) { return exp_fast(y * log_fast(x)); }
+CLOUDSC_FN float pow_fast(float x, float y) { return pw(x, y); }
+/* sqrt(x) for normal x > 0: MUFU.RSQ64H seed, two Newton steps on 1/sqrt, one on the root */
+CLOUDSC_FN double sqrt_fast(double x) {
+#if defined(__CUDACC__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-h * r, r, 0.5);
+  r = fma(r, e, r);
+  const double q = x * r;
+  return fma(fma(-q, q, x), 0.5 * r, q);
+#else
+  return std::sqrt(x);
+#endif
+}
+CLOUDSC_FN float sqrt_fast(float x) { return sq(x); }
+
 #if CLOUDSC_STRICT
 #define CLOUDSC_RCP(x) (one / (x))
 #define CLOUDSC_DIV(a, b) ((a) / (b))
 #define CLOUDSC_DIVR(a, b, r) ((a) / (b))  /* a/b where r == 1/b is available in fast mode */
+#define CLOUDSC_POW(x, y) pw(x, y)
+#define CLOUDSC_SQRT(x) sq(x)
+template <typename T> CLOUDSC_FN T pow15(T x) { return pw(x, T(1.5)); }
+template <typename T> CLOUDSC_FN T cube(T x) { return pw(x, T(3.0)); }
+#define CLOUDSC_POW15(x) pow15<T>(x)
+#define CLOUDSC_CUBE(x) cube<T>(x)
 template <typename T> CLOUDSC_FN T ex(T x) { return ex_lib(x); }
 #else
 #define CLOUDSC_RCP(x) rcp_fast(x)
 #define CLOUDSC_DIV(a, b) ((a) * rcp_fast(b))
 #define CLOUDSC_DIVR(a, b, r) ((a) * (r))
+#define CLOUDSC_POW(x, y) pow_fast(x, y)
+#define CLOUDSC_SQRT(x) sqrt_fast(x)
+template <typename T> CLOUDSC_FN T pow15(T x) { return x * sqrt_fast(x); }
+template <typename T> CLOUDSC_FN T cube(T x) { return (x * x) * x; }
+#define CLOUDSC_POW15(x) pow15<T>(x)
+#define CLOUDSC_CUBE(x) cube<T>(x)
 template <typename T> CLOUDSC_FN T ex(T x) { return exp_fast(x); }
 #endif
 
@@ -285,24 +357,22 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
     T qv = io.template ld<IN_PQ>(k) + ptsphy * io.template ld<IN_TQ>(k);
     T a = io.template ld<IN_PA>(k) + ptsphy * io.template ld<IN_TA>(k);
     const T aorig = a;
-    T qx[4], qx0[4], lneg[4];
+    T qx[4], qx0[4];
     qx[0] = io.template ld<IN_PCLV0>(k) + ptsphy * io.template ld<IN_TCLD0>(k);
     qx[1] = io.template ld<IN_PCLV1>(k) + ptsphy * io.template ld<IN_TCLD1>(k);
     qx[2] = io.template ld<IN_PCLV2>(k) + ptsphy * io.template ld<IN_TCLD2>(k);
     qx[3] = io.template ld<IN_PCLV3>(k) + ptsphy * io.template ld<IN_TCLD3>(k);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) { qx0[m] = qx[m]; lneg[m] = zero; }
+    for (int m = 0; m < 4; ++m) qx0[m] = qx[m];
     T tend_t = zero, tend_q = zero;
 
     /* ---- tidy up very small cloud cover / condensate, :519-541 */
     if (qx[0] + qx[1] < c.rlmin || a < c.ramin) {
-      lneg[0] = lneg[0] + qx[0];
       T qadj = qx[0] * zqtmst;
       tend_q = tend_q + qadj;
       tend_t = tend_t - c.ralvdcp * qadj;
       qv = qv + qx[0];
       qx[0] = zero;
-      lneg[1] = lneg[1] + qx[1];
       qadj = qx[1] * zqtmst;
       tend_q = tend_q + qadj;
       tend_t = tend_t - c.ralsdcp * qadj;
@@ -314,7 +384,6 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       if (qx[m] < c.rlmin) {
-        lneg[m] = lneg[m] + qx[m];
         const T qadj = qx[m] * zqtmst;
         tend_q = tend_q + qadj;
         tend_t = tend_t - ((m & 1) ? c.ralsdcp : c.ralvdcp) * qadj;
@@ -362,11 +431,15 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 
       /* ================= 3.0 initialise, :739-859 ========================================= */
       T qxfg[4] = {qx[0], qx[1], qx[2], qx[3]};
-      T qa[5][5], qb03 = zero, qb13 = zero, qb00 = zero, qb11 = zero;
-#pragma unroll
-      for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = 0; j < 5; ++j) qa[i][j] = zero;
+      /* ZSOLQA (:742-750).  Every process of the scheme enters it as an antisymmetric pair
+       * zsolqa[x][y] += v; zsolqa[y][x] -= v (a transfer between two species) or as a diagonal source,
+       * and the sink limiter scales both members of a pair by the same factor, so zsolqa[y][x] ==
+       * -zsolqa[x][y] holds bit for bit (IEEE addition and multiplication are sign-symmetric).  Only
+       * the upper triangle a_xy = zsolqa[x][y] (x < y; 0=l 1=i 2=r 3=s 4=v; the pair (i,s) is never
+       * written) and the diagonal d_m are kept: 13 instead of 25 values in registers. */
+      T a01 = zero, a02 = zero, a03 = zero, a04 = zero, a12 = zero, a14 = zero, a23 = zero, a24 = zero, a34 = zero;
+      T d0 = zero, d1 = zero, d2 = zero, d3 = zero;
+      T qb03 = zero, qb13 = zero, qb00 = zero, qb11 = zero;
       T solab = zero, solac = zero;
       T convsrce0 = zero, convsrce1 = zero, psupsrce0 = zero, psupsrce1 = zero;
       T convsink = zero; /* zconvsink[l] == zconvsink[i] */
@@ -413,8 +486,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       (void)r_1ma;
 
       /* evaporate very small amounts of liquid and ice, :847-857 */
-      if (qx[0] < c.rlmin) { qa[0][4] = qx[0]; qa[4][0] = -qx[0]; }
-      if (qx[1] < c.rlmin) { qa[1][4] = qx[1]; qa[4][1] = -qx[1]; }
+      if (qx[0] < c.rlmin) a04 = qx[0];
+      if (qx[1] < c.rlmin) a14 = qx[1];
 
       /* ================= 3.1 ice supersaturation adjustment, :879-952 ===================== */
       const T fokoop = mn(c.rkoop1 - c.rkoop2 * t, CLOUDSC_DIV(c.r2es * e_liq, c.r2es * e_ice));
@@ -430,14 +503,14 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           supsat = mx(CLOUDSC_DIVR(one_m_a * (qp1env - fac * qsice), corqsice, r_corqsice), zero);
         }
         if (supsat > c.zepsec) {
-          if (t > c.rthomo) { qa[4][0] = qa[4][0] + supsat; qa[0][4] = qa[0][4] - supsat; qxfg[0] = qxfg[0] + supsat; }
-          else              { qa[4][1] = qa[4][1] + supsat; qa[1][4] = qa[1][4] - supsat; qxfg[1] = qxfg[1] + supsat; }
+          if (t > c.rthomo) { a04 = a04 - supsat; qxfg[0] = qxfg[0] + supsat; }
+          else              { a14 = a14 - supsat; qxfg[1] = qxfg[1] + supsat; }
           solac = one_m_a * facI;
         }
         const T psupsat = io.template ld<IN_PSUPSAT>(k);
         if (psupsat > c.zepsec) {
-          if (t > c.rthomo) { qa[0][0] = qa[0][0] + psupsat; psupsrce0 = psupsat; qxfg[0] = qxfg[0] + psupsat; }
-          else              { qa[1][1] = qa[1][1] + psupsat; psupsrce1 = psupsat; qxfg[1] = qxfg[1] + psupsat; }
+          if (t > c.rthomo) { d0 = d0 + psupsat; psupsrce0 = psupsat; qxfg[0] = qxfg[0] + psupsat; }
+          else              { d1 = d1 + psupsat; psupsrce1 = psupsat; qxfg[1] = qxfg[1] + psupsat; }
           solac = one_m_a * facI;
         }
       }
@@ -450,12 +523,12 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           solac = solac + CLOUDSC_DIV(plude_out, plu_n);
           convsrce0 = alfa_w * plude_out;
           convsrce1 = (one - alfa_w) * plude_out;
-          qa[0][0] = qa[0][0] + convsrce0;
-          qa[1][1] = qa[1][1] + convsrce1;
+          d0 = d0 + convsrce0;
+          d1 = d1 + convsrce1;
         } else {
           plude_out = zero;
         }
-        qa[3][3] = qa[3][3] + io.template ld<IN_PSNDE>(k) * dtgdp;
+        d3 = d3 + io.template ld<IN_PSNDE>(k) * dtgdp;
       }
 
       /* ================= 3.3 subsidence compensating convective updraughts, :1002-1075 ==== */
@@ -474,12 +547,12 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           T evap = mn(lcust0 - lfinal, evaplimmix);
           lfinal = lcust0 - evap;
           lfinalsum = lfinalsum + lfinal;
-          qa[0][0] = qa[0][0] + lcust0; qa[0][4] = qa[0][4] + evap; qa[4][0] = qa[4][0] - evap;
+          d0 = d0 + lcust0; a04 = a04 + evap;
           lfinal = mx(zero, lcust1 - dqs_s);
           evap = mn(lcust1 - lfinal, evaplimmix);
           lfinal = lcust1 - evap;
           lfinalsum = lfinalsum + lfinal;
-          qa[1][1] = qa[1][1] + lcust1; qa[1][4] = qa[1][4] + evap; qa[4][1] = qa[4][1] - evap;
+          d1 = d1 + lcust1; a14 = a14 + evap;
         }
         if (lfinalsum < c.zepsec) acust = zero;
         solac = solac + acust;
@@ -502,8 +575,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           leros = mn(leros, li);
           const T aeros = CLOUDSC_DIV(leros, licld);
           solac = solac - aeros;
-          qa[0][4] = qa[0][4] + liqfrac * leros; qa[4][0] = qa[4][0] - liqfrac * leros;
-          qa[1][4] = qa[1][4] + icefrac * leros; qa[4][1] = qa[4][1] - icefrac * leros;
+          a04 = a04 + liqfrac * leros;
+          a14 = a14 + icefrac * leros;
         }
       }
 
@@ -530,8 +603,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         T levap = a * mn(dqs, licld);
         levap = mn(levap, evaplimmix);
         levap = mn(levap, mx(qsmix - qv, zero));
-        qa[0][4] = qa[0][4] + liqfrac * levap; qa[4][0] = qa[4][0] - liqfrac * levap;
-        qa[1][4] = qa[1][4] + icefrac * levap; qa[4][1] = qa[4][1] - icefrac * levap;
+        a04 = a04 + liqfrac * levap;
+        a14 = a14 + icefrac * levap;
       }
       /* 3.4b (1) increase of cloud water in existing clouds, :1214-1248 */
       if (dqs <= -c.rlmin && a > c.zepsec) {
@@ -551,8 +624,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         lcond1 = mx(mn(lcond1, cdmax), zero);
         lcond1 = a * lcond1;
         if (lcond1 < c.rlmin) lcond1 = zero;
-        if (t > c.rthomo) { qa[4][0] = qa[4][0] + lcond1; qa[0][4] = qa[0][4] - lcond1; qxfg[0] = qxfg[0] + lcond1; }
-        else              { qa[4][1] = qa[4][1] + lcond1; qa[1][4] = qa[1][4] - lcond1; qxfg[1] = qxfg[1] + lcond1; }
+        if (t > c.rthomo) { a04 = a04 - lcond1; qxfg[0] = qxfg[0] + lcond1; }
+        else              { a14 = a14 - lcond1; qxfg[1] = qxfg[1] + lcond1; }
       }
       /* 3.4b (2) generation of new clouds, :1254-1361 */
       if (dqs <= -c.rlmin && a < sc.one_m_zepsec) {
@@ -582,8 +655,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           if (one_m_a < c.zepsec || lcond2 < c.rlmin) { lcond2 = zero; acond = zero; }
           if (lcond2 == zero) acond = zero;
           solac = solac + acond;
-          if (t > c.rthomo) { qa[4][0] = qa[4][0] + lcond2; qa[0][4] = qa[0][4] - lcond2; qxfg[0] = qxfg[0] + lcond2; }
-          else              { qa[4][1] = qa[4][1] + lcond2; qa[1][4] = qa[1][4] - lcond2; qxfg[1] = qxfg[1] + lcond2; }
+          if (t > c.rthomo) { a04 = a04 - lcond2; qxfg[0] = qxfg[0] + lcond2; }
+          else              { a14 = a14 - lcond2; qxfg[1] = qxfg[1] + lcond2; }
         }
       }
 
@@ -606,15 +679,15 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 #else
         const T add = (c.rlstt * ((c.rlstt * c.r_rv) * r_t - one)) * (c.r_p0024 * r_t);
         const T bdd = ((c.rv * t) * pap) * rcp_fast(c.p221 * vpice);
-        const T cvds = ((c.p78 * pw(icenuclei * r_rho, c.p0666)) * (vpliq - vpice)) * rcp_fast((c.p887 * (add + bdd)) * vpice);
+        const T cvds = ((c.p78 * CLOUDSC_POW(icenuclei * r_rho, c.p0666)) * (vpliq - vpice)) * rcp_fast((c.p887 * (add + bdd)) * vpice);
         const T ice0 = mx(icecld, (icenuclei * c.riceinit) * r_rho);
 #endif
-        const T inew = pw((c.p0666 * cvds) * ptsphy + pw(ice0, c.p0666), T(1.5));
+        const T inew = CLOUDSC_POW15((c.p0666 * cvds) * ptsphy + CLOUDSC_POW(ice0, c.p0666));
         T depos = mx(a * (inew - ice0), zero);
         depos = mn(depos, qxfg[0]);
         const T infactor = mn(CLOUDSC_DIVR(icenuclei, T(15000.0), c.r_15000), one);
         depos = depos * mn(infactor + (one - infactor) * (c.rdepliqrefrate + CLOUDSC_DIVR(s.cldtopdist, c.rdepliqrefdepth, c.r_rdepliqrefdepth)), one);
-        qa[0][1] = qa[0][1] + depos; qa[1][0] = qa[1][0] - depos;
+        a01 = a01 + depos;
         qxfg[1] = qxfg[1] + depos; qxfg[0] = qxfg[0] - depos;
       }
 
@@ -627,9 +700,9 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       T qpretot = zero;
       T fallsrce1 = zero, fallsrce2 = zero, fallsrce3 = zero;
       if (k > ktop) {
-        fallsrce1 = s.pf_i * dtgdp; qa[1][1] = qa[1][1] + fallsrce1; qxfg[1] = qxfg[1] + fallsrce1; qpretot = qpretot + qxfg[1];
-        fallsrce2 = s.pf_r * dtgdp; qa[2][2] = qa[2][2] + fallsrce2; qxfg[2] = qxfg[2] + fallsrce2; qpretot = qpretot + qxfg[2];
-        fallsrce3 = s.pf_s * dtgdp; qa[3][3] = qa[3][3] + fallsrce3; qxfg[3] = qxfg[3] + fallsrce3; qpretot = qpretot + qxfg[3];
+        fallsrce1 = s.pf_i * dtgdp; d1 = d1 + fallsrce1; qxfg[1] = qxfg[1] + fallsrce1; qpretot = qpretot + qxfg[1];
+        fallsrce2 = s.pf_r * dtgdp; d2 = d2 + fallsrce2; qxfg[2] = qxfg[2] + fallsrce2; qpretot = qpretot + qxfg[2];
+        fallsrce3 = s.pf_s * dtgdp; d3 = d3 + fallsrce3; qxfg[3] = qxfg[3] + fallsrce3; qpretot = qpretot + qxfg[3];
       }
       const T fallsink1 = dtgdp * (c.rvice * rho);
       const T fallsink2 = dtgdp * (c.rvrain * rho);
@@ -663,29 +736,27 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       if (liqcld > c.zepsec) {
         T rainaut, rainacc;
         if (liqcld > lcrit_kk) {
-          rainaut = ((((T(1.5) * a) * ptsphy) * c.rcl_kkaau) * pw(liqcld, c.rcl_kkbauq)) * kk_num_pow;
+          rainaut = ((((T(1.5) * a) * ptsphy) * c.rcl_kkaau) * CLOUDSC_POW(liqcld, c.rcl_kkbauq)) * kk_num_pow;
           rainaut = mn(rainaut, qxfg[0]);
           if (rainaut < c.zepsec) rainaut = zero;
-          rainacc = (((T(2.0) * a) * ptsphy) * c.rcl_kkaac) * pw(liqcld * raincld, c.rcl_kkbac);
+          rainacc = (((T(2.0) * a) * ptsphy) * c.rcl_kkaac) * CLOUDSC_POW(liqcld * raincld, c.rcl_kkbac);
           rainacc = mn(rainacc, qxfg[0]);
           if (rainacc < c.zepsec) rainacc = zero;
         } else {
           rainaut = zero; rainacc = zero;
         }
         if (t <= c.rtt) {
-          qa[0][3] = qa[0][3] + rainaut; qa[0][3] = qa[0][3] + rainacc;
-          qa[3][0] = qa[3][0] - rainaut; qa[3][0] = qa[3][0] - rainacc;
+          a03 = a03 + rainaut; a03 = a03 + rainacc;
         } else {
-          qa[0][2] = qa[0][2] + rainaut; qa[0][2] = qa[0][2] + rainacc;
-          qa[2][0] = qa[2][0] - rainaut; qa[2][0] = qa[2][0] - rainacc;
+          a02 = a02 + rainaut; a02 = a02 + rainacc;
         }
       }
       /* riming of snow by cloud water, :1771-1785 */
       if (t <= c.rtt && liqcld > c.zepsec) {
         if (s.covptot > c.p001 && snowcld > c.zepsec) {
-          const T fallcorr = pw(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
+          const T fallcorr = CLOUDSC_POW(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
           T snowrime = ((((c.p03 * s.covptot) * ptsphy) * c.rcl_const7s) * fallcorr) *
-                       pw((rho * snowcld) * c.rcl_const1s, c.rcl_const8s);
+                       CLOUDSC_POW((rho * snowcld) * c.rcl_const1s, c.rcl_const8s);
           snowrime = mn(snowrime, one);
           qb03 = qb03 + snowrime;
         }
@@ -707,11 +778,11 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           T alfa = CLOUDSC_DIVR(qxfg[1], icetot, r_icetot);
           T melt = mn(qxfg[1], alfa * meltmax);
           qxfg[1] = qxfg[1] - melt; qxfg[2] = qxfg[2] + melt;
-          qa[1][2] = qa[1][2] + melt; qa[2][1] = qa[2][1] - melt;
+          a12 = a12 + melt;
           alfa = CLOUDSC_DIVR(qxfg[3], icetot, r_icetot);
           melt = mn(qxfg[3], alfa * meltmax);
           qxfg[3] = qxfg[3] - melt; qxfg[2] = qxfg[2] + melt;
-          qa[3][2] = qa[3][2] + melt; qa[2][3] = qa[2][3] - melt;
+          a23 = a23 - melt;
         }
       }
       /* 4.4b freezing of rain, :1866-1906 */
@@ -723,9 +794,9 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         if (t < c.rtt) {
           T frzmax;
           if (s.rainfrac > c.p08) {
-            const T lambda = pw(CLOUDSC_DIV(c.rcl_fac1, rho * qx[2]), c.rcl_fac2);
+            const T lambda = CLOUDSC_POW(CLOUDSC_DIV(c.rcl_fac1, rho * qx[2]), c.rcl_fac2);
             const T temp = c.rcl_fzrab * (t - c.rtt);
-            const T frz = ((ptsphy * CLOUDSC_DIVR(c.rcl_const5r, rho, r_rho)) * (ex(temp) - one)) * pw(lambda, c.rcl_const6r);
+            const T frz = ((ptsphy * CLOUDSC_DIVR(c.rcl_const5r, rho, r_rho)) * (ex(temp) - one)) * CLOUDSC_POW(lambda, c.rcl_const6r);
             frzmax = mx(frz, zero);
           } else {
             const T cons1 = ab(CLOUDSC_DIVR(ptsphy * (one + T(0.5) * (c.rtt - t)), c.rtaumel, c.r_rtaumel));
@@ -733,7 +804,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           }
           if (frzmax > c.zepsec) {
             const T frz = mn(qx[2], frzmax);
-            qa[2][3] = qa[2][3] + frz; qa[3][2] = qa[3][2] - frz;
+            a23 = a23 + frz;
           }
         }
       }
@@ -742,7 +813,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         const T frzmax = mx((c.rthomo - t) * sc.zrldcp, zero);
         if (frzmax > c.zepsec && qxfg[0] > c.zepsec) {
           const T frz = mn(qxfg[0], frzmax);
-          qa[0][1] = qa[0][1] + frz; qa[1][0] = qa[1][0] - frz;
+          a01 = a01 + frz;
         }
       }
       /* 4.5 evaporation of rain, Abel & Boutle, :1984-2038 */
@@ -754,19 +825,19 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         const T qe = mx(zero, mn(qv, qsliq));
         if (covpclr > c.zepsec && qxfg[2] > c.zepsec && qe < zzrh * qsliq) {
           const T preclr = CLOUDSC_DIV(qxfg[2], s.covptot);
-          const T fallcorr = pw(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
+          const T fallcorr = CLOUDSC_POW(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
           const T esatliq = sc.rv_rd * (c.r2es * e_liq);
-          const T lambda = pw(CLOUDSC_DIV(c.rcl_fac1, rho * preclr), c.rcl_fac2);
-          const T evap_denom = c.rcl_cdenom1 * esatliq - c.rcl_cdenom2 * t * esatliq + (c.rcl_cdenom3 * pw(t, T(3.0))) * pap;
-          const T corr2 = CLOUDSC_DIV(pw(CLOUDSC_DIVR(t, T(273.0), c.r_273), T(1.5)) * T(393.0), t + T(120.0));
+          const T lambda = CLOUDSC_POW(CLOUDSC_DIV(c.rcl_fac1, rho * preclr), c.rcl_fac2);
+          const T evap_denom = c.rcl_cdenom1 * esatliq - c.rcl_cdenom2 * t * esatliq + (c.rcl_cdenom3 * CLOUDSC_CUBE(t)) * pap;
+          const T corr2 = CLOUDSC_DIV(CLOUDSC_POW15(CLOUDSC_DIVR(t, T(273.0), c.r_273)) * T(393.0), t + T(120.0));
           const T subsat = mx(zzrh * qsliq - qe, zero);
           const T beta = ((((CLOUDSC_DIV(T(0.5), qsliq) * (t * t)) * esatliq) * c.rcl_const1r) * CLOUDSC_DIV(corr2, evap_denom)) *
-                         (CLOUDSC_DIV(c.p078, pw(lambda, c.rcl_const4r)) +
-                          CLOUDSC_DIV(c.rcl_const2r * sq(rho * fallcorr), sq(corr2) * pw(lambda, c.rcl_const3r)));
+                         (CLOUDSC_DIV(c.p078, CLOUDSC_POW(lambda, c.rcl_const4r)) +
+                          CLOUDSC_DIV(c.rcl_const2r * CLOUDSC_SQRT(rho * fallcorr), CLOUDSC_SQRT(corr2) * CLOUDSC_POW(lambda, c.rcl_const3r)));
           const T denom = one + beta * ptsphy;
           const T dpevap = CLOUDSC_DIV(((covpclr * beta) * ptsphy) * subsat, denom);
           const T evap = mn(dpevap, qxfg[2]);
-          qa[2][4] = qa[2][4] + evap; qa[4][2] = qa[4][2] - evap;
+          a24 = a24 + evap;
           s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, CLOUDSC_DIV((s.covptot - a) * evap, qxfg[2])));
           qxfg[2] = qxfg[2] - evap;
         }
@@ -779,20 +850,20 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         if (covpclr > c.zepsec && qxfg[3] > c.zepsec && qe < zzrh * qsice) {
           const T cd = s.covptot * dtgdp;
           const T preclr = CLOUDSC_DIV(qxfg[3] * covpclr, cs(mx(ab(cd), c.zepsilon), cd));
-          const T beta1 = CLOUDSC_DIV(CLOUDSC_DIVR(sq(CLOUDSC_DIVR(pap, paph_surf, r_paph_surf)), c.rvrfactor, c.r_rvrfactor) * preclr, mx(covpclr, c.zepsec));
-          const T beta = sc.rg_rpecons * pw(beta1, c.p05777);
+          const T beta1 = CLOUDSC_DIV(CLOUDSC_DIVR(CLOUDSC_SQRT(CLOUDSC_DIVR(pap, paph_surf, r_paph_surf)), c.rvrfactor, c.r_rvrfactor) * preclr, mx(covpclr, c.zepsec));
+          const T beta = sc.rg_rpecons * CLOUDSC_POW(beta1, c.p05777);
           const T denom = one + (beta * ptsphy) * corqsice;
           const T dpr = (CLOUDSC_DIV((covpclr * beta) * (qsice - qe), denom) * dp) * sc.zrg_r;
           const T dpevap = dpr * dtgdp;
           const T evap = mn(dpevap, qxfg[3]);
-          qa[3][4] = qa[3][4] + evap; qa[4][3] = qa[4][3] - evap;
+          a34 = a34 + evap;
           s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, CLOUDSC_DIV((s.covptot - a) * evap, qxfg[3])));
           qxfg[3] = qxfg[3] - evap;
         }
       }
       /* evaporate small precipitation amounts, :2144-2158 */
-      if (qxfg[2] < c.rlmin) { qa[2][4] = qa[2][4] + qxfg[2]; qa[4][2] = qa[4][2] - qxfg[2]; }
-      if (qxfg[3] < c.rlmin) { qa[3][4] = qa[3][4] + qxfg[3]; qa[4][3] = qa[4][3] - qxfg[3]; }
+      if (qxfg[2] < c.rlmin) { a24 = a24 + qxfg[2]; }
+      if (qxfg[3] < c.rlmin) { a34 = a34 + qxfg[3]; }
 
       /* ================= 5.1 solver for cloud cover, :2168-2180 =========================== */
       T anew = CLOUDSC_DIV(a + solac, one + solab);
@@ -805,57 +876,82 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* (the first pass :2207-2227 is overwritten before use).  zratio = zmm/max(zsinksum,zmm) is
        * exactly 1 unless the sinks of species m exceed its content, and scaling by 1 is the
        * identity -- so the divide and the scaling only run in that case. */
-      const T qx5[5] = {qx[0], qx[1], qx[2], qx[3], qv};
-#pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        T psum = zero;
-#pragma unroll
-        for (int n = 0; n < 5; ++n) psum = psum + qa[n][m];
-        const T sinksum = zero - psum;
-        const T mm = mx(qx5[m], c.zepsec);
+      /* column sums sum_n zsolqa[n][m], n = 0..4 in the reference's order (:2239, :2330) */
+#define CLOUDSC_COLSUM0 ((((zero + d0) - a01) - a02) - a03) - a04
+#define CLOUDSC_COLSUM1 (((zero + a01) + d1) - a12) - a14
+#define CLOUDSC_COLSUM2 ((((zero + a02) + a12) + d2) - a23) - a24
+#define CLOUDSC_COLSUM3 (((zero + a03) + a23) + d3) - a34
+#define CLOUDSC_COLSUM4 (((zero + a04) + a14) + a24) + a34
+      /* "if zsolqa[n][m] < 0 scale the pair": a_nm itself for n < m, a_mn > 0 for n > m; a negative
+       * diagonal is scaled twice (n == m hits both statements of :2281-2282) */
+#define CLOUDSC_SCALE_LO(a) if ((a) < zero) (a) = (a) * ratio
+#define CLOUDSC_SCALE_HI(a) if ((a) > zero) (a) = (a) * ratio
+#define CLOUDSC_SCALE_D(d) if ((d) < zero) (d) = ((d) * ratio) * ratio
+      {
+        T mm = mx(qx[0], c.zepsec), sinksum = zero - (CLOUDSC_COLSUM0);
         if (sinksum > mm) {
           const T ratio = CLOUDSC_DIV(mm, sinksum);
-#pragma unroll
-          for (int n = 0; n < 5; ++n) {
-            if (qa[n][m] < zero) {
-              qa[n][m] = qa[n][m] * ratio;
-              qa[m][n] = qa[m][n] * ratio;
-            }
-          }
+          CLOUDSC_SCALE_D(d0); CLOUDSC_SCALE_HI(a01); CLOUDSC_SCALE_HI(a02); CLOUDSC_SCALE_HI(a03); CLOUDSC_SCALE_HI(a04);
+        }
+        mm = mx(qx[1], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM1);
+        if (sinksum > mm) {
+          const T ratio = CLOUDSC_DIV(mm, sinksum);
+          CLOUDSC_SCALE_LO(a01); CLOUDSC_SCALE_D(d1); CLOUDSC_SCALE_HI(a12); CLOUDSC_SCALE_HI(a14);
+        }
+        mm = mx(qx[2], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM2);
+        if (sinksum > mm) {
+          const T ratio = CLOUDSC_DIV(mm, sinksum);
+          CLOUDSC_SCALE_LO(a02); CLOUDSC_SCALE_LO(a12); CLOUDSC_SCALE_D(d2); CLOUDSC_SCALE_HI(a23); CLOUDSC_SCALE_HI(a24);
+        }
+        mm = mx(qx[3], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM3);
+        if (sinksum > mm) {
+          const T ratio = CLOUDSC_DIV(mm, sinksum);
+          CLOUDSC_SCALE_LO(a03); CLOUDSC_SCALE_LO(a23); CLOUDSC_SCALE_D(d3); CLOUDSC_SCALE_HI(a34);
+        }
+        mm = mx(qv, c.zepsec); sinksum = zero - (CLOUDSC_COLSUM4);
+        if (sinksum > mm) {
+          const T ratio = CLOUDSC_DIV(mm, sinksum);
+          CLOUDSC_SCALE_LO(a04); CLOUDSC_SCALE_LO(a14); CLOUDSC_SCALE_LO(a24); CLOUDSC_SCALE_LO(a34);
         }
       }
 
       /* ================= 5.2.2 implicit solve, :2294-2397 ================================= */
       /*
-       * RHS :2326-2337.  LHS: diag d_m = 1 + fallsink_m + sum_n qb[m][n], off-diagonals -qb[m][n];
+       * RHS :2326-2337.  LHS: diag den_m = 1 + fallsink_m + sum_n qb[m][n], off-diagonals -qb[m][n];
        * the only non-zero qb are (l,l) (i,i) (l,s) (i,s), i.e. the transposed system is lower
        * triangular with the single sub-diagonal row "snow <- liquid, ice".  The reference's
-       * non-pivoting LU then produces exactly two multipliers, -qb03/d0 and -qb13/d1, leaves
+       * non-pivoting LU then produces exactly two multipliers, -qb03/den0 and -qb13/den1, leaves
        * every diagonal unchanged, and the back-substitution is a plain divide per species.
        */
       T qxn[5];
-#pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        T expl = zero;
-#pragma unroll
-        for (int n = 0; n < 5; ++n) expl = expl + qa[n][m];
-        qxn[m] = qx5[m] + expl;
-      }
+      qxn[0] = qx[0] + (CLOUDSC_COLSUM0);
+      qxn[1] = qx[1] + (CLOUDSC_COLSUM1);
+      qxn[2] = qx[2] + (CLOUDSC_COLSUM2);
+      qxn[3] = qx[3] + (CLOUDSC_COLSUM3);
+      qxn[4] = qv + (CLOUDSC_COLSUM4);
+#undef CLOUDSC_COLSUM0
+#undef CLOUDSC_COLSUM1
+#undef CLOUDSC_COLSUM2
+#undef CLOUDSC_COLSUM3
+#undef CLOUDSC_COLSUM4
+#undef CLOUDSC_SCALE_LO
+#undef CLOUDSC_SCALE_HI
+#undef CLOUDSC_SCALE_D
       {
-        const T d0 = ((one + zero) + qb00) + qb03;
-        const T d1 = ((one + fallsink1) + qb11) + qb13;
-        const T d2 = one + fallsink2;
-        const T d3 = one + fallsink3;
-        const T r_d0 = CLOUDSC_RCP(d0), r_d1 = CLOUDSC_RCP(d1);
-        (void)r_d0; (void)r_d1;
-        const T l03 = CLOUDSC_DIVR(-qb03, d0, r_d0);
-        const T l13 = CLOUDSC_DIVR(-qb13, d1, r_d1);
+        const T den0 = ((one + zero) + qb00) + qb03;
+        const T den1 = ((one + fallsink1) + qb11) + qb13;
+        const T den2 = one + fallsink2;
+        const T den3 = one + fallsink3;
+        const T r_den0 = CLOUDSC_RCP(den0), r_den1 = CLOUDSC_RCP(den1);
+        (void)r_den0; (void)r_den1;
+        const T l03 = CLOUDSC_DIVR(-qb03, den0, r_den0);
+        const T l13 = CLOUDSC_DIVR(-qb13, den1, r_den1);
         qxn[3] = qxn[3] - l03 * qxn[0];
         qxn[3] = qxn[3] - l13 * qxn[1];
-        qxn[3] = CLOUDSC_DIV(qxn[3], d3);
-        qxn[2] = CLOUDSC_DIV(qxn[2], d2);
-        qxn[1] = CLOUDSC_DIVR(qxn[1], d1, r_d1);
-        qxn[0] = CLOUDSC_DIVR(qxn[0], d0, r_d0);
+        qxn[3] = CLOUDSC_DIV(qxn[3], den3);
+        qxn[2] = CLOUDSC_DIV(qxn[2], den2);
+        qxn[1] = CLOUDSC_DIVR(qxn[1], den1, r_den1);
+        qxn[0] = CLOUDSC_DIVR(qxn[0], den0, r_den0);
       }
       /* clip small/negative values into vapour, :2402-2412 */
 #pragma unroll
@@ -912,16 +1008,17 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 
       const T gdph_r = (sc.neg_zrg_r * (paph_n - s.paph_k)) * zqtmst;
       const T pvfl = io.template ld<IN_PVFL>(k), pvfi = io.template ld<IN_PVFI>(k);
-      /* rain/snow rows copy the liquid/ice running sums of the level above (:2550-2555) */
+      /* rain/snow rows copy the liquid/ice running sums of the level above (:2550-2555).
+       * zlneg[m] (:526,550: the condensate removed by the tidy-up, else 0) == qx0[m] - qx[m] exactly. */
       const T fsqrf = s.fsqlf + (qxn2d[2] - qx0[2]) * gdph_r;
-      const T fcqrng = s.fcqlng + lneg[2] * gdph_r;
+      const T fcqrng = s.fcqlng + (qx0[2] - qx[2]) * gdph_r;
       const T fsqsf = s.fsqif + (qxn2d[3] - qx0[3]) * gdph_r;
-      const T fcqsng = s.fcqnng + lneg[3] * gdph_r;
+      const T fcqsng = s.fcqnng + (qx0[3] - qx[3]) * gdph_r;
       s.fsqlf = s.fsqlf + (qxn2d[0] - qx0[0] + pvfl * ptsphy - alfa_w * plude_out) * gdph_r;
-      s.fcqlng = s.fcqlng + lneg[0] * gdph_r;
+      s.fcqlng = s.fcqlng + (qx0[0] - qx[0]) * gdph_r;
       s.fsqltur = s.fsqltur + (pvfl * ptsphy) * gdph_r;
       s.fsqif = s.fsqif + (qxn2d[1] - qx0[1] + pvfi * ptsphy - (one - alfa_w) * plude_out) * gdph_r;
-      s.fcqnng = s.fcqnng + lneg[1] * gdph_r;
+      s.fcqnng = s.fcqnng + (qx0[1] - qx[1]) * gdph_r;
       s.fsqitur = s.fsqitur + (pvfi * ptsphy) * gdph_r;
       io.template st<OUT_FSQLF>(k + 1, s.fsqlf);   io.template st<OUT_FSQIF>(k + 1, s.fsqif);
       io.template st<OUT_FSQRF>(k + 1, fsqrf);     io.template st<OUT_FSQSF>(k + 1, fsqsf);

@@ -256,6 +256,121 @@ cloudsc_sweep_tile(const __grid_constant__ FieldTable ft, const LaunchGeom g, co
   cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
 }
 
+/* ---- IO policy 3: thread-private cp.async ring, pre-offset slot pointers, streaming stores -------- */
+/*
+ * Every thread stages ITS OWN column: per level 27 `cp.async` (SASS LDGSTS, 8 bytes each, a warp
+ * instruction moves one coalesced 256-byte row) copy the inputs of level k+2 into the thread's slots
+ * of a 2-stage shared-memory ring while level k is computed; `cp.async.wait_group 1` at the top of a
+ * level is the only synchronisation -- no barrier, no mbarrier, no coupling between threads, any
+ * NPROMA / column range.  The consumer reads a slot with one LDS at an immediate offset.
+ *
+ * Address arithmetic is reduced to one 64-bit add per access: the host folds everything that does
+ * not depend on the thread (species offset inside [nclv][klev][nproma] fields, the +1 row of the
+ * fields consumed one level ahead / of the [klev+1] flux outputs) into a table of 27 + 24 slot
+ * pointers passed in the kernel-parameter bank, and the thread keeps three running byte offsets
+ * (one per field kind) that it bumps by one row per level.
+ */
+struct SlotTable {
+  const void *in[N_IN];   /* (field, species, row shift) of every input slot */
+  void *out[N_OUT];       /* same for the output slots */
+  const void *paph, *plsm;
+  const int *ktype;
+  void *rainfrac;
+};
+
+/* 1 for the output slots written at row k+1 (the [klev+1] flux fields) */
+__host__ __device__ constexpr int out_next(int s) { return s >= OUT_FSQLF ? 1 : 0; }
+
+template <typename T> __device__ __forceinline__ void cp_async_elem(unsigned dst, const void *src);
+template <> __device__ __forceinline__ void cp_async_elem<double>(unsigned dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+template <> __device__ __forceinline__ void cp_async_elem<float>(unsigned dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+template <typename T, int BLOCK>
+struct PipeIO {
+  static constexpr int kRow = BLOCK * (int)sizeof(T);      /* bytes between two slots of a thread */
+  static constexpr int kStage = N_IN * kRow;
+  static constexpr int kSmem = 2 * kStage;
+  const SlotTable &tab;
+  long long bL, bH, bC;     /* byte offsets of (block, current level, this column) per field kind */
+  long long b1;             /* element offset of the per-column scalars */
+  long long rowb;           /* nproma * sizeof(T) */
+  int klev;
+  unsigned sm_t;            /* shared address of this thread's slot 0 of stage 0 */
+  const T *st_t;            /* generic pointer to the same */
+  const T *cur;             /* this thread's slot 0 of the stage being consumed */
+
+  /* queue the inputs of `level`; (pL, pH, pC) = byte offsets of that level */
+  __device__ __forceinline__ void issue(int level, long long pL, long long pH, long long pC) {
+    if (level < klev) {
+      const unsigned dst = sm_t + ((unsigned)level & 1u) * (unsigned)kStage;
+      const bool has_next = level + 1 < klev;   /* pmfu/pmfd/plu have no row klev; it is never consumed */
+#pragma unroll
+      for (int s = 0; s < N_IN; ++s) {
+        const long long off = in_kind(s) == 0 ? pL : in_kind(s) == 1 ? pH : pC;
+        if (s == IN_PAPH || !in_next(s) || has_next)
+          cp_async_elem<T>(dst + (unsigned)(s * kRow), static_cast<const char *>(tab.in[s]) + off);
+      }
+    }
+    cp_async_commit();   /* one group per level, empty past the last one: keeps wait_group 1 exact */
+  }
+  __device__ __forceinline__ void prologue() {
+    issue(0, bL, bH, bC);
+    issue(1, bL + rowb, bH + rowb, bC + rowb);
+  }
+  __device__ __forceinline__ void level_begin(int k) {
+    cur = st_t + (k & 1) * (kStage / (int)sizeof(T));
+    cp_async_wait1();
+  }
+  __device__ __forceinline__ void level_end(int k) {
+    issue(k + 2, bL + 2 * rowb, bH + 2 * rowb, bC + 2 * rowb);
+    bL += rowb; bH += rowb; bC += rowb;
+  }
+  template <int S> __device__ __forceinline__ T ld(int) const { return cur[S * BLOCK]; }
+  template <int S> __device__ __forceinline__ T ld_next(int) const { return cur[S * BLOCK]; }
+  __device__ __forceinline__ T paph_row(int r) const {
+    return __ldg(reinterpret_cast<const T *>(static_cast<const char *>(tab.paph) + bH + (long long)r * rowb));
+  }
+  template <int S> __device__ __forceinline__ void st(int, T v) {
+    const long long off = out_kind(S) == 0 ? bL : out_kind(S) == 1 ? bH : bC;
+    __stcs(reinterpret_cast<T *>(static_cast<char *>(tab.out[S]) + off), v);
+  }
+  /* row 0 of a flux field: tab.out carries the +1 row of the in-loop stores */
+  template <int S> __device__ __forceinline__ void st_row0(T v) {
+    __stcs(reinterpret_cast<T *>(static_cast<char *>(tab.out[S]) + (bH - rowb)), v);
+  }
+  __device__ __forceinline__ T plsm() const { return __ldg(static_cast<const T *>(tab.plsm) + b1); }
+  __device__ __forceinline__ int ktype() const { return __ldg(tab.ktype + b1); }
+  __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(tab.rainfrac)[b1] = v; }
+};
+
+template <typename T, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+cloudsc_sweep_pipe(const __grid_constant__ SlotTable tab, const LaunchGeom g, const __grid_constant__ StepConst<T> sc) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using IO = PipeIO<T, BLOCK>;
+  const int col = g.col_begin + blockIdx.x * BLOCK + threadIdx.x;
+  if (col >= g.col_end) return;
+  const int ibl = col / g.nproma;
+  const int jl = col - ibl * g.nproma;
+  const long long eL = (long long)ibl * g.klev * g.nproma;
+  IO io{tab,
+        (eL + jl) * (long long)sizeof(T),
+        ((long long)ibl * (g.klev + 1) * g.nproma + jl) * (long long)sizeof(T),
+        (eL * 5 + jl) * (long long)sizeof(T),
+        (long long)ibl * g.nproma + jl,
+        (long long)g.nproma * (long long)sizeof(T), g.klev,
+        smem_u32(smem_raw) + threadIdx.x * (unsigned)sizeof(T),
+        reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr};
+  io.prologue();
+  cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+}
+
 /* ---- host side -------------------------------------------------------------------------------- */
 /* host mirrors of the constant blocks of the current device (per-launch constants derive from them) */
 static CloudscConst<double> h_const64[64];
@@ -385,10 +500,60 @@ cudaError_t launch_tile(const FieldTable &ft, const LaunchGeom &g, double ptsphy
   void *args[] = {(void *)&ft, (void *)&g, (void *)&sc};
   return cudaLaunchKernel(fn, dim3(grid), dim3(per_cta), args, smem, stream);
 }
+
+/* ---- pipe (cp.async) variant ---------------------------------------------------------------------- */
+constexpr int kPipeBlock = 32;
+inline bool is_pipe(int variant) { return variant >= VARIANT_PIPE_W12 && variant <= VARIANT_PIPE_W16; }
+inline int pipe_wps(int variant) { return variant == VARIANT_PIPE_W8 ? 8 : variant == VARIANT_PIPE_W16 ? 16 : 12; }
+
+template <typename T>
+SlotTable make_slot_table(const FieldTable &ft, const LaunchGeom &g) {
+  SlotTable t;
+  const long long row = g.nproma, sp = (long long)g.klev * g.nproma;
+  for (int s = 0; s < N_IN; ++s)
+    t.in[s] = static_cast<const char *>(ft.p[in_field(s)]) + (in_species(s) * sp + in_next(s) * row) * (long long)sizeof(T);
+  for (int s = 0; s < N_OUT; ++s)
+    t.out[s] = static_cast<char *>(ft.p[out_field(s)]) + (out_species(s) * sp + out_next(s) * row) * (long long)sizeof(T);
+  t.paph = ft.p[CLOUDSC_F_PAPH];
+  t.plsm = ft.p[CLOUDSC_F_PLSM];
+  t.ktype = static_cast<const int *>(ft.p[CLOUDSC_F_KTYPE]);
+  t.rainfrac = ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ];
+  return t;
+}
+
+template <typename T>
+const void *pipe_fn(int wps) {
+  switch (wps) {
+    case 8: return (const void *)cloudsc_sweep_pipe<T, kPipeBlock, 8>;
+    case 16: return (const void *)cloudsc_sweep_pipe<T, kPipeBlock, 16>;
+    default: return (const void *)cloudsc_sweep_pipe<T, kPipeBlock, 12>;
+  }
+}
+
+template <typename T>
+cudaError_t launch_pipe(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int variant, cudaStream_t stream) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const void *fn = pipe_fn<T>(pipe_wps(variant));
+  const size_t smem = PipeIO<T, kPipeBlock>::kSmem;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  const int ncols = g.col_end - g.col_begin;
+  const int grid = (ncols + kPipeBlock - 1) / kPipeBlock;
+  SlotTable tab = make_slot_table<T>(ft, g);
+  StepConst<T> sc;
+  fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
+  void *args[] = {(void *)&tab, (void *)&g, (void *)&sc};
+  return cudaLaunchKernel(fn, dim3(grid), dim3(kPipeBlock), args, smem, stream);
+}
 }  // namespace
 
 template <typename T>
 static cudaError_t launch_any(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int variant, cudaStream_t stream) {
+  if (is_pipe(variant)) return launch_pipe<T>(ft, g, ptsphy, variant, stream);
   const TileCfg cfg = tile_cfg(variant, g.nproma);
   if (is_tile(variant) && tile_ok<T>(ft, g, cfg)) {
     /* the TMA kernel moves whole rows of 32*WARPS columns: give it the aligned part of the range and
@@ -423,11 +588,18 @@ cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsph
 
 cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]) {
   const TileCfg cfg = tile_cfg(variant, nproma);
-  const bool tile = is_tile(variant) && cfg.warps > 0;
+  const bool pipe = is_pipe(variant);
+  const bool tile = pipe || (is_tile(variant) && cfg.warps > 0);   /* "uses dynamic shared memory" */
   cudaFuncAttributes a;
   size_t dyn = 0;
-  const void *fn = precision == CLOUDSC_B200_FP32 ? (tile ? tile_fn<float>(cfg, &dyn) : direct_fn<float>(variant))
-                                                  : (tile ? tile_fn<double>(cfg, &dyn) : direct_fn<double>(variant));
+  const void *fn;
+  if (pipe) {
+    fn = precision == CLOUDSC_B200_FP32 ? pipe_fn<float>(pipe_wps(variant)) : pipe_fn<double>(pipe_wps(variant));
+    dyn = precision == CLOUDSC_B200_FP32 ? PipeIO<float, kPipeBlock>::kSmem : PipeIO<double, kPipeBlock>::kSmem;
+  } else {
+    fn = precision == CLOUDSC_B200_FP32 ? (tile ? tile_fn<float>(cfg, &dyn) : direct_fn<float>(variant))
+                                        : (tile ? tile_fn<double>(cfg, &dyn) : direct_fn<double>(variant));
+  }
   cudaError_t e;
   if (tile) {
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -437,7 +609,7 @@ cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]
   }
   e = cudaFuncGetAttributes(&a, fn);
   if (e != cudaSuccess) return e;
-  const int threads = tile ? cfg.warps * 32 : kDirectBlock;
+  const int threads = pipe ? kPipeBlock : tile ? cfg.warps * 32 : kDirectBlock;
   int nb = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, dyn);
   if (e != cudaSuccess) return e;

@@ -38,6 +38,10 @@ enum Variant {
   VARIANT_TILE_C4_W16 = 6,
   VARIANT_TILE_C1_W12 = 7,  /* one-warp CTAs, warp-private tiles; the default (VARIANT_AUTO) */
   VARIANT_TILE_C2_W12 = 8,
+  /* thread-private cp.async ring (LDGSTS), pre-offset slot pointers, streaming stores; any geometry */
+  VARIANT_PIPE_W12 = 9,
+  VARIANT_PIPE_W8 = 10,
+  VARIANT_PIPE_W16 = 11,
   VARIANT_COUNT
 };
 

@@ -173,7 +173,7 @@ def test_unsupported_params_fail_loudly(built, input_data):
     assert ei.value.code == -1 and "laericesed" in str(ei.value)
 
 
-@pytest.mark.parametrize("kernel_variant", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("kernel_variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 def test_every_kernel_variant_matches_oracle(built, oracle, input_data, kernel_variant):
     """All register-budget / IO-policy variants run the same arithmetic: each must meet the parity bar on
     a ragged geometry (last block partly filled, column count not a multiple of the warp size)."""
