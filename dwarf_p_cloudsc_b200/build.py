@@ -20,6 +20,7 @@ LIBDIR = os.path.join(PKG, "lib")
 INC = os.path.join(ROOT, "include")
 LIB = os.path.join(LIBDIR, "libcloudsc_b200.so")
 DRIVER = os.path.join(LIBDIR, "dwarf-cloudsc-b200")
+HOSTLIB = os.path.join(LIBDIR, "libcloudsc_host.so")   # loader + validator as a library (ctypes tests)
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 HOSTCC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"   # $CC here is a wrapper without libgomp
@@ -77,9 +78,21 @@ def build_driver(force=False, verbose=False):
     return DRIVER
 
 
+def build_hostlib(force=False, verbose=False):
+    """load_state / load_reference / cloudsc_validate / h5lite as a shared object, so that the CPU tests
+    can drive the C loader and validator through ctypes (the driver executable links the same sources)."""
+    srcs = [os.path.join(HOST, f) for f in ("load_state.c", "cloudsc_validate.c", "h5lite.c", "mycpu.c")]
+    headers = _glob(HOST, (".h",)) + _glob(INC, (".h",))
+    if force or _newer(HOSTLIB, srcs + headers + [LIB]):
+        _run([HOSTCC, "-std=c11", "-O2", "-fopenmp", "-fPIC", "-shared", f"-I{INC}", f"-I{HOST}", *srcs, "-o", HOSTLIB,
+              f"-L{LIBDIR}", "-lcloudsc_b200", "-Wl,-rpath,$ORIGIN", "-lm"], verbose)
+    return HOSTLIB
+
+
 def build_all(force=False, verbose=False):
     lib = build_library(force, verbose)
     drv = build_driver(force, verbose)
+    build_hostlib(force, verbose)
     return lib, drv
 
 

@@ -121,6 +121,34 @@ size_t cloudsc_b200_field_block_elems(int f, int nproma, int klev) {
   return rows_of(f, klev) * (size_t)nproma;
 }
 
+int cloudsc_b200_set_device(int device) {
+  CU(cudaSetDevice(device));
+  return 0;
+}
+
+int cloudsc_b200_host_alloc(void **out, size_t bytes) {
+  if (!out) return fail(CLOUDSC_B200_EARG, "host_alloc: out is NULL");
+  *out = nullptr;
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return 0;
+}
+
+int cloudsc_b200_host_free(void *p) {
+  if (p) CU(cudaFreeHost(p));
+  return 0;
+}
+
+int cloudsc_b200_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return 0;
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+
+int cloudsc_b200_host_unregister(void *p) {
+  if (p) CU(cudaHostUnregister(p));
+  return 0;
+}
+
 int cloudsc_b200_set_params(const struct TECLDP *p, const struct cloudsc_consts *k) {
   if (!p || !k) return fail(CLOUDSC_B200_EARG, "set_params: NULL argument");
   if (const char *why = check_params(p)) return fail(CLOUDSC_B200_EPARAMS, "unsupported parameter set: %s", why);

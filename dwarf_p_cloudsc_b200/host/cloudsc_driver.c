@@ -1,0 +1,174 @@
+/*
+ * cloudsc_driver.c -- the dwarf-cloudsc-c driver (reference: src/cloudsc_c/cloudsc/cloudsc_driver.c)
+ * with the OpenMP block loop (:183-229) replaced by the B200 library.
+ *
+ * Kept from the reference: the field set and its allocation sizes (:119-179), query_state / load_state,
+ * the replication of the 100 input columns, the zeroing contract of pcovptot / tend_loc_cld (done
+ * inside the kernel), the performance table (NUMOMP .. col/s, "@ core#" rows and the TOTAL row,
+ * MFlops/s from the 12 482 329 flop / 100 columns model, :232-259) and cloudsc_validate().
+ * Changed: host fields live in page-locked memory; each of the NUMOMP "threads" is one GPU owning a
+ * contiguous range of NPROMA blocks (nblocks/ngpu each, the last one takes the remainder --
+ * src/cloudsc_fortran/dwarf_cloudsc.F90:74-77); the timed region of the table is the kernel sweep on
+ * device-resident fields (what the reference's GPU variants time), and a second TOTAL row reports the
+ * same run including the H2D upload and D2H download.
+ */
+#include "cloudsc_driver.h"
+
+#include <omp.h>
+
+#include "mycpu.h"
+
+static int g_status = 0;
+int cloudsc_driver_status(void) { return g_status; }
+
+#define MAXGPU 64
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    int rc_ = (call);                                                                               \
+    if (rc_ != 0) {                                                                                 \
+      fprintf(stderr, "cloudsc_driver: %s failed (%d): %s\n", #call, rc_, cloudsc_b200_last_error()); \
+      g_status = rc_;                                                                               \
+      failed = 1;                                                                                   \
+    }                                                                                               \
+  } while (0)
+
+static void *pinned(size_t bytes) {
+  void *p = NULL;
+  if (cloudsc_b200_host_alloc(&p, bytes) != 0) {
+    fprintf(stderr, "cloudsc_driver: cannot allocate %zu bytes of page-locked memory: %s\n", bytes, cloudsc_b200_last_error());
+    exit(2);
+  }
+  return p;
+}
+
+void cloudsc_driver(int numthreads, int numcols, int nproma) {
+  void *F[CLOUDSC_NFIELDS];
+  double ptsphy;
+  int klon, nlev;
+  const double zhpm = 12482329.0;  /* IBM P7 HPM flop count for 100 points at L137 (cloudsc_driver.c:101) */
+
+  g_status = 0;
+  if (numcols <= 0 || nproma <= 0) { fprintf(stderr, "cloudsc_driver: NGPTOT and NPROMA must be positive\n"); g_status = CLOUDSC_B200_EARG; return; }
+  const int nblocks = numcols / nproma + (numcols % nproma ? 1 : 0);
+  int ngpu = cloudsc_b200_device_count();
+  if (ngpu <= 0) { fprintf(stderr, "cloudsc_driver: no CUDA device (%s); the CLOUDSC hot path has no CPU fallback\n", cloudsc_b200_last_error()); g_status = ngpu ? ngpu : CLOUDSC_B200_ENOTINIT; return; }
+  if (numthreads > 0 && numthreads < ngpu) ngpu = numthreads;
+  if (ngpu > nblocks) ngpu = nblocks;
+  if (ngpu > MAXGPU) ngpu = MAXGPU;
+  numthreads = ngpu;
+
+  nclv = 5; ncldql = 1; ncldqi = 2; ncldqr = 3; ncldqs = 4; ncldqv = 5;   /* cloudsc_driver.c:103-108 */
+  yrecldp = malloc(sizeof(struct TECLDP));
+
+  query_state(&klon, &nlev);
+
+  /* every field of the cloudsc_c() argument list, sized as the reference sizes it; the kernel never
+   * touches the N/A fields but the driver contract allocates and loads them, so we do too */
+  for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
+    const size_t elems = (size_t)nblocks * cloudsc_b200_field_block_elems(f, nproma, nlev);
+    F[f] = pinned(elems * (cloudsc_b200_field_kind(f) == 'I' ? sizeof(int) : sizeof(double)));
+  }
+#define P(name) ((double *)F[CLOUDSC_F_##name])
+  load_state(klon, nlev, nclv, numcols, nproma, &ptsphy, P(PLCRIT_AER), P(PICRIT_AER), P(PRE_ICE), P(PCCN), P(PNICE),
+             P(PT), P(PQ), P(TENDENCY_CML_T), P(TENDENCY_CML_Q), P(TENDENCY_CML_A), P(TENDENCY_CML_CLD),
+             P(TENDENCY_TMP_T), P(TENDENCY_TMP_Q), P(TENDENCY_TMP_A), P(TENDENCY_TMP_CLD), P(PVFA), P(PVFL), P(PVFI),
+             P(PDYNA), P(PDYNL), P(PDYNI), P(PHRSW), P(PHRLW), P(PVERVEL), P(PAP), P(PAPH), P(PLSM),
+             (int *)F[CLOUDSC_F_KTYPE], P(PLU), P(PLUDE), P(PSNDE), P(PMFU), P(PMFD), P(PA), P(PCLV), P(PSUPSAT));
+
+  double zinfo[5][MAXGPU];
+  int failed = 0;
+  const double t0 = omp_get_wtime();
+  double t_kernel_begin = 0.0, t_kernel_end = 0.0;
+
+#pragma omp parallel num_threads(ngpu) default(shared)
+  {
+    const int tid = omp_get_thread_num();
+    const int per = nblocks / ngpu;
+    const int b0 = tid * per;
+    const int nb = tid == ngpu - 1 ? nblocks - b0 : per;          /* last GPU takes the remainder */
+    long long c1 = (long long)(b0 + nb) * nproma;
+    if (c1 > numcols) c1 = numcols;
+    const int ncols = (int)(c1 - (long long)b0 * nproma);
+    void *slice[CLOUDSC_NFIELDS];
+    for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
+      const size_t blk = cloudsc_b200_field_block_elems(f, nproma, nlev) * (cloudsc_b200_field_kind(f) == 'I' ? sizeof(int) : sizeof(double));
+      slice[f] = (char *)F[f] + (size_t)b0 * blk;
+    }
+    cloudsc_b200_state *st = NULL;
+    CK(cloudsc_b200_set_device(tid));
+    CK(cloudsc_b200_set_params_from_globals());
+    CK(cloudsc_b200_create(ncols, nproma, nlev, CLOUDSC_B200_FP64, &st));
+    if (st) {
+      CK(cloudsc_b200_upload(st, slice, NULL));
+      CK(cloudsc_b200_step(st, ptsphy, 0, 0, NULL));   /* warm-up launch (module load, clocks) */
+      CK(cloudsc_b200_reset_inout(st, NULL));          /* PLUDE is in/out: restore it for the timed run */
+      CK(cloudsc_b200_sync(NULL));
+    }
+#pragma omp barrier
+#pragma omp master
+    t_kernel_begin = omp_get_wtime();
+    const double start = omp_get_wtime();
+    if (st) {
+      CK(cloudsc_b200_step(st, ptsphy, 0, 0, NULL));
+      CK(cloudsc_b200_sync(NULL));
+    }
+    const double end = omp_get_wtime();
+#pragma omp barrier
+#pragma omp master
+    t_kernel_end = omp_get_wtime();
+    if (st) {
+      CK(cloudsc_b200_download(st, slice, NULL));
+      CK(cloudsc_b200_sync(NULL));
+      cloudsc_b200_destroy(st);
+    }
+    zinfo[0][tid] = end - start;
+    zinfo[1][tid] = (double)mycpu();
+    zinfo[2][tid] = (double)nb;
+    zinfo[3][tid] = (double)ncols;
+    zinfo[4][tid] = (double)tid;
+  }
+  const double t3 = omp_get_wtime();
+  if (failed) { fprintf(stderr, "cloudsc_driver: GPU run failed, no results\n"); goto done; }
+
+  printf("     NUMOMP=%d, NGPTOT=%d, NPROMA=%d, NGPBLKS=%d\n", numthreads, numcols, nproma, nblocks);
+  printf(" Reference MFLOP count for 100 columns : %12.8f\n", 1.0e-06 * zhpm);
+  printf(" %10s%10s%10s%10s%10s %4s : %10s%10s%10s\n", "NUMOMP", "NGPTOT", "#GP-cols", "#BLKS", "NPROMA", "tid#",
+         "Time(msec)", "MFlops/s", "col/s");
+  double zmflops = 0.0, zthrput = 0.0;
+  for (int t = 0; t < numthreads; ++t) {
+    const double tloc = zinfo[0][t];
+    const int igpc = (int)zinfo[3][t];
+    if (tloc > 0.0) {
+      zmflops = 1.0e-06 * zhpm * ((double)igpc / 100.) / tloc;
+      zthrput = (double)igpc / tloc;
+    } else {
+      zmflops = 0.; zthrput = 0.;
+    }
+    printf(" %10d%10d%10d%10d%10d %4d : %10.3f%10d%10d @ core#%d gpu#%d\n", numthreads, numcols, igpc, (int)zinfo[2][t], nproma, t,
+           tloc * 1000., (int)zmflops, (int)zthrput, (int)zinfo[1][t], (int)zinfo[4][t]);
+  }
+  {
+    const double tdiff = t_kernel_end - t_kernel_begin;
+    zmflops = tdiff > 0.0 ? 1.0e-06 * zhpm * ((double)numcols / 100.) / tdiff : 0.0;
+    zthrput = tdiff > 0.0 ? (double)numcols / tdiff : 0.0;
+    printf(" %10d%10d%10d%10d%10d %4d : %10.3f%10d%10d TOTAL\n", numthreads, numcols, numcols, nblocks, nproma, -1,
+           tdiff * 1000., (int)zmflops, (int)zthrput);
+    const double tall = t3 - t0;
+    printf(" %10d%10d%10d%10d%10d %4d : %10.3f%10d%10d TOTAL incl. create+H2D+warm-up+D2H\n", numthreads, numcols, numcols,
+           nblocks, nproma, -2, tall * 1000., (int)(1.0e-06 * zhpm * ((double)numcols / 100.) / tall), (int)((double)numcols / tall));
+  }
+
+  cloudsc_validate(klon, nlev, nclv, numcols, nproma, P(PLUDE), P(PCOVPTOT), P(PRAINFRAC_TOPRFZ), P(PFSQLF), P(PFSQIF),
+                   P(PFCQLNG), P(PFCQNNG), P(PFSQRF), P(PFSQSF), P(PFCQRNG), P(PFCQSNG), P(PFSQLTUR), P(PFSQITUR),
+                   P(PFPLSL), P(PFPLSN), P(PFHPSL), P(PFHPSN), P(TENDENCY_LOC_A), P(TENDENCY_LOC_Q), P(TENDENCY_LOC_T),
+                   P(TENDENCY_LOC_CLD));
+  if (cloudsc_validate_failures() > 0) {
+    fprintf(stderr, "cloudsc_driver: %d field(s) outside the parity bar\n", cloudsc_validate_failures());
+    g_status = 1;
+  }
+#undef P
+done:
+  for (int f = 0; f < CLOUDSC_NFIELDS; ++f) cloudsc_b200_host_free(F[f]);
+  free(yrecldp);
+  yrecldp = NULL;
+}

@@ -91,6 +91,17 @@ char cloudsc_b200_field_use(int f);
 /* elements one NPROMA block of field f holds (e.g. klev*nproma) */
 size_t cloudsc_b200_field_block_elems(int f, int nproma, int klev);
 
+/* ---- devices and pinned host memory ------------------------------------------------------- */
+/* select the CUDA device of the calling host thread (one handle / one host thread per GPU;
+ * successor of the implicit device 0 of src/cloudsc_cuda/cloudsc/cloudsc_driver.cu) */
+int cloudsc_b200_set_device(int device);
+/* page-locked host memory for the field arrays (what makes H2D/D2H asynchronous; the reference
+ * driver uses plain malloc, cloudsc_driver.c:119-179) -- or pin memory the caller already owns */
+int cloudsc_b200_host_alloc(void **out, size_t bytes);
+int cloudsc_b200_host_free(void *p);
+int cloudsc_b200_host_register(void *p, size_t bytes);
+int cloudsc_b200_host_unregister(void *p);
+
 /* ---- parameters -> __constant__ memory of the current device ---------------------------- */
 int cloudsc_b200_set_params(const struct TECLDP *ydecldp, const struct cloudsc_consts *consts);
 /* convenience for C callers that use the reference's globals (yrecldp, rg, r2es, ...) */

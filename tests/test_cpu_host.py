@@ -1,0 +1,129 @@
+"""CPU tests of the C host side (host/load_state.c, cloudsc_validate.c, h5lite.c) through ctypes:
+the loader must build exactly the arrays the reference loader builds (restated in NumPy by
+dwarf_p_cloudsc_b200.state), the validator must reproduce the dwarf's table semantics."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+@pytest.fixture(scope="module")
+def hostlib(built):
+    os.environ["CLOUDSC_INPUT_H5"] = os.path.join(GOLDEN, "input.h5")
+    os.environ["CLOUDSC_REFERENCE_H5"] = os.path.join(GOLDEN, "reference.h5")
+    from dwarf_p_cloudsc_b200 import api  # noqa: F401  (loads libcloudsc_b200.so first: it owns the globals)
+    lib = ctypes.CDLL(os.path.join(ROOT, "dwarf_p_cloudsc_b200", "lib", "libcloudsc_host.so"))
+    lib.h5lite_open.restype = ctypes.c_void_p
+    lib.h5lite_open.argtypes = [ctypes.c_char_p]
+    lib.h5lite_close.argtypes = [ctypes.c_void_p]
+    lib.h5lite_count.restype = ctypes.c_size_t
+    lib.h5lite_count.argtypes = [ctypes.c_void_p]
+    lib.h5lite_name.restype = ctypes.c_char_p
+    lib.h5lite_name.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    lib.h5lite_read_double.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _dp, ctypes.c_size_t]
+    lib.h5lite_read_int.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_size_t]
+    lib.h5lite_error.restype = ctypes.c_char_p
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_c_h5lite_matches_python_h5lite(hostlib):
+    from dwarf_p_cloudsc_b200 import h5lite
+    for fn in ("input.h5", "reference.h5"):
+        path = os.path.join(GOLDEN, fn)
+        py = h5lite.read_h5(path)
+        f = hostlib.h5lite_open(path.encode())
+        assert f, hostlib.h5lite_error()
+        names = {hostlib.h5lite_name(f, i).decode() for i in range(hostlib.h5lite_count(f))}
+        assert names == set(py)
+        for name, a in py.items():
+            out = np.empty(a.size, dtype=np.float64)
+            assert hostlib.h5lite_read_double(f, name.encode(), out.ctypes.data_as(_dp), a.size) == 0, name
+            assert np.array_equal(out, a.reshape(-1).astype(np.float64)), name
+        iout = np.empty(100, dtype=np.int32)
+        if "KTYPE" in py:
+            assert hostlib.h5lite_read_int(f, b"/KTYPE", iout.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 100) == 0
+            assert np.array_equal(iout, py["KTYPE"])
+        # errors are reported, not crashed on
+        assert hostlib.h5lite_read_double(f, b"NO_SUCH_DATASET", out.ctypes.data_as(_dp), 1) == -1
+        assert hostlib.h5lite_read_double(f, b"PLUDE", out.ctypes.data_as(_dp), 3) == -1
+        hostlib.h5lite_close(f)
+    assert not hostlib.h5lite_open(b"/nonexistent/file.h5")
+    assert not hostlib.h5lite_open(os.path.join(ROOT, "bench.py").encode())   # not an HDF5 file
+
+
+@pytest.mark.parametrize("ngptot,nproma,first", [(100, 100, 0), (257, 32, 0), (1000, 128, 0), (300, 64, 1234567)])
+def test_c_load_state_matches_numpy_restatement(hostlib, ngptot, nproma, first):
+    from dwarf_p_cloudsc_b200 import api, params, state
+    cols, scalars, klon, klev = state.load_input()
+    kl, kv = ctypes.c_int(), ctypes.c_int()
+    hostlib.query_state(ctypes.byref(kl), ctypes.byref(kv))
+    assert (kl.value, kv.value) == (klon, klev)
+
+    want = state.blocked_fields(cols, ngptot, nproma, klev, first_column=first, live_only=False)
+    got = {n: np.full_like(a, -7) for n, a in want.items()}
+    p = params.TECLDP()
+    ctypes.c_void_p.in_dll(api.lib, "yrecldp").value = ctypes.addressof(p)
+    pts = ctypes.c_double()
+    order = ["PLCRIT_AER", "PICRIT_AER", "PRE_ICE", "PCCN", "PNICE", "PT", "PQ", "TENDENCY_CML_T", "TENDENCY_CML_Q",
+             "TENDENCY_CML_A", "TENDENCY_CML_CLD", "TENDENCY_TMP_T", "TENDENCY_TMP_Q", "TENDENCY_TMP_A", "TENDENCY_TMP_CLD",
+             "PVFA", "PVFL", "PVFI", "PDYNA", "PDYNL", "PDYNI", "PHRSW", "PHRLW", "PVERVEL", "PAP", "PAPH", "PLSM", "KTYPE",
+             "PLU", "PLUDE", "PSNDE", "PMFU", "PMFD", "PA", "PCLV", "PSUPSAT"]      # load_state.h:24-32
+    hostlib.load_state_set_first_column(ctypes.c_longlong(first))
+    try:
+        hostlib.load_state(klon, klev, 5, ngptot, nproma, ctypes.byref(pts), *[_ptr(got[n]) for n in order])
+    finally:
+        hostlib.load_state_set_first_column(ctypes.c_longlong(0))
+    assert pts.value == scalars["PTSPHY"]
+    for n in order:
+        assert np.array_equal(got[n], want[n]), n
+    # parameters: *yrecldp and the YOMCST/YOETHF globals
+    pw, kw = params.params_from_scalars(scalars)
+    assert bytes(p) == bytes(pw)
+    for n in params.KERNEL_CONSTS:
+        assert ctypes.c_double.in_dll(api.lib, n).value == getattr(kw, n), n
+    ctypes.c_void_p.in_dll(api.lib, "yrecldp").value = None
+
+
+def test_c_validate_reference_against_itself_and_detects_errors(hostlib, capfd):
+    from dwarf_p_cloudsc_b200 import state
+    ngptot, nproma, klev = 257, 32, 137
+    ref = state.load_reference()
+    order = ["PLUDE", "PCOVPTOT", "PRAINFRAC_TOPRFZ", "PFSQLF", "PFSQIF", "PFCQLNG", "PFCQNNG", "PFSQRF", "PFSQSF",
+             "PFCQRNG", "PFCQSNG", "PFSQLTUR", "PFSQITUR", "PFPLSL", "PFPLSN", "PFHPSL", "PFHPSN", "TENDENCY_LOC_A",
+             "TENDENCY_LOC_Q", "TENDENCY_LOC_T", "TENDENCY_LOC_CLD"]               # cloudsc_validate.h:16-20
+    F = {n: state.expand(ref[n], ngptot, nproma) for n in order}
+    hostlib.cloudsc_validate(100, klev, 5, ngptot, nproma, *[_ptr(F[n]) for n in order])
+    out = capfd.readouterr().out
+    assert hostlib.cloudsc_validate_failures() == 0
+    lines = [l for l in out.splitlines() if "2D" in l]
+    assert len(lines) == 21 and all("2D1" in l and "PASS" in l for l in lines)      # iopt 1: zerrsum < eps
+    assert lines[0].split()[0] == "PLUDE" and lines[-1].split()[0] == "TENDENCY_LOC%CLD"
+    # one wrong value in a valid column is found; the same error in a padding column is not looked at
+    F["PFHPSN"][0, 100, 3] += 1.0e-3
+    F["TENDENCY_LOC_T"][-1, 50, nproma - 1] += 1.0      # block 8 holds columns 256..287, only 256 is valid
+    hostlib.cloudsc_validate(100, klev, 5, ngptot, nproma, *[_ptr(F[n]) for n in order])
+    out = capfd.readouterr().out
+    assert hostlib.cloudsc_validate_failures() == 1
+    bad = [l for l in out.splitlines() if "FAIL" in l]
+    assert len(bad) == 1 and bad[0].split()[0] == "PFHPSN" and "2D3" in bad[0]      # |ref| up to 84: integer abs() sum > 0
+
+
+def test_driver_executable_fails_loudly_without_a_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    exe = os.path.join(ROOT, "dwarf_p_cloudsc_b200", "lib", "dwarf-cloudsc-b200")
+    r = subprocess.run([exe, "1", "100", "16"], cwd=GOLDEN, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    r = subprocess.run([exe, "1", "2"], cwd=GOLDEN, capture_output=True, text=True)
+    assert r.returncode != 0 and "right number of arguments" in r.stdout

@@ -191,3 +191,18 @@ def test_every_kernel_variant_matches_oracle(built, oracle, input_data, kernel_v
             _compare(G, R, ngptot)
     finally:
         api.set_variant(0)
+
+
+@pytest.mark.parametrize("args", [("1", "100", "16"), ("1", "16384", "128"), ("1", "1000", "100")])
+def test_c_driver_executable_validates_against_reference_h5(built, args):
+    """dwarf-cloudsc-b200 NUMOMP NGPTOT NPROMA: the C host (load_state from input.h5, GPU sweep,
+    cloudsc_validate against reference.h5) -- the dwarf-cloudsc-c command line end to end."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "dwarf_p_cloudsc_b200", "lib", "dwarf-cloudsc-b200")
+    r = subprocess.run([exe, *args], cwd=os.path.join(root, "tests", "golden"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    rows = [l for l in r.stdout.splitlines() if " 2D" in l]
+    assert len(rows) == 21 and all(l.rstrip().endswith("PASS") for l in rows), r.stdout
+    assert "TOTAL" in r.stdout and f"NGPTOT={args[1]}, NPROMA={args[2]}" in r.stdout
