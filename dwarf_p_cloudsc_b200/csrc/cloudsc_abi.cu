@@ -294,13 +294,83 @@ void *cloudsc_b200_field_ptr(cloudsc_b200_state *st, int f) {
 /* host-resident fields: chunked multi-stream pipeline                                            */
 /* ---------------------------------------------------------------------------------------------- */
 namespace {
+/*
+ * Per-device pipeline resources, kept between calls: cudaMalloc/cudaFree cost ~1 ms / ~0.4 ms each on
+ * B200 (tools/ubench/pcie.cu), which for 51 fields x 3 lanes would be twice the time the copies
+ * themselves need.  One arena per lane, carved into the live fields at 256-byte boundaries.
+ */
+constexpr int kMaxLanes = 8;
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
-  void *dev[CLOUDSC_NFIELDS] = {nullptr};
+  char *arena = nullptr;
   bool used = false;
 };
+struct Pipe {
+  std::mutex mu;
+  int nlanes = 0;
+  size_t lane_bytes = 0;
+  Lane lanes[kMaxLanes];
+  cudaEvent_t w0 = nullptr, w1 = nullptr;
+  void release() {
+    for (int i = 0; i < kMaxLanes; ++i) {
+      Lane &l = lanes[i];
+      if (l.arena) cudaFree(l.arena);
+      if (l.k0) cudaEventDestroy(l.k0);
+      if (l.k1) cudaEventDestroy(l.k1);
+      if (l.stream) cudaStreamDestroy(l.stream);
+      l = Lane();
+    }
+    if (w0) cudaEventDestroy(w0);
+    if (w1) cudaEventDestroy(w1);
+    w0 = w1 = nullptr;
+    nlanes = 0;
+    lane_bytes = 0;
+  }
+};
+Pipe g_pipes[64];
+
+cudaError_t pipe_reserve(Pipe &p, int nlanes, size_t lane_bytes) {
+  cudaError_t e;
+  if (!p.w0) {
+    if ((e = cudaEventCreate(&p.w0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&p.w1)) != cudaSuccess) return e;
+  }
+  for (int i = 0; i < nlanes; ++i) {
+    Lane &l = p.lanes[i];
+    if (!l.stream) {
+      if ((e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+      if ((e = cudaEventCreate(&l.k0)) != cudaSuccess) return e;
+      if ((e = cudaEventCreate(&l.k1)) != cudaSuccess) return e;
+    }
+    if (!l.arena || lane_bytes > p.lane_bytes) {
+      if (l.arena) cudaFree(l.arena);
+      l.arena = nullptr;
+      if ((e = cudaMalloc(&l.arena, lane_bytes)) != cudaSuccess) return e;
+    }
+    l.used = false;
+  }
+  if (lane_bytes > p.lane_bytes) {
+    /* lanes beyond nlanes keep smaller arenas: drop them so that lane_bytes describes every arena */
+    for (int i = nlanes; i < kMaxLanes; ++i)
+      if (p.lanes[i].arena) { cudaFree(p.lanes[i].arena); p.lanes[i].arena = nullptr; }
+    p.lane_bytes = lane_bytes;
+  } else {
+    for (int i = 0; i < nlanes; ++i)
+      if (!p.lanes[i].arena) return cudaErrorMemoryAllocation;
+  }
+  if (nlanes > p.nlanes) p.nlanes = nlanes;
+  return cudaSuccess;
+}
 }  // namespace
+
+int cloudsc_b200_release_cache(void) {
+  for (auto &p : g_pipes) {
+    std::lock_guard<std::mutex> lk(p.mu);
+    p.release();
+  }
+  return 0;
+}
 
 int cloudsc_b200_run_host(void *const host[CLOUDSC_NFIELDS], int ngptot, int nproma, int klev, double ptsphy,
                           int chunk_blocks, int nstreams, double stats[4]) {
@@ -308,53 +378,54 @@ int cloudsc_b200_run_host(void *const host[CLOUDSC_NFIELDS], int ngptot, int npr
   if (int rc = check_fields(host)) return rc;
   if (int rc = current_device_ready()) return rc;
   const int nblocks = (ngptot + nproma - 1) / nproma;
-  if (nstreams <= 0) nstreams = 3;
+  if (nstreams <= 0) nstreams = 4;
+  if (nstreams > kMaxLanes) nstreams = kMaxLanes;
   if (chunk_blocks <= 0) {
-    /* ~8 chunks per stream, at least 148*2 CUDA blocks of work per chunk when the problem allows */
-    chunk_blocks = (nblocks + nstreams * 8 - 1) / (nstreams * 8);
-    const int min_blocks = (296 * 128 + nproma - 1) / nproma;
+    /* ~6 chunks per lane: pipeline fill (first upload) and drain (last kernel + download) stay
+       below ~5 % of the transfer time.  The kernel is ~2.5 % of a chunk's copy time, so chunks are
+       sized for overlap, not for kernel occupancy; the floor only avoids degenerate launches. */
+    chunk_blocks = (nblocks + nstreams * 6 - 1) / (nstreams * 6);
+    const int min_blocks = (4096 + nproma - 1) / nproma;
     if (chunk_blocks < min_blocks) chunk_blocks = min_blocks;
   }
   if (chunk_blocks > nblocks) chunk_blocks = nblocks;
   const int nchunks = (nblocks + chunk_blocks - 1) / chunk_blocks;
   if (nstreams > nchunks) nstreams = nchunks;
 
-  std::vector<Lane> lanes(nstreams);
-  int rc = 0;
+  /* arena layout of one lane */
+  size_t off[CLOUDSC_NFIELDS], blk[CLOUDSC_NFIELDS], lane_bytes = 0;
+  for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
+    off[f] = 0;
+    blk[f] = rows_of(f, klev) * nproma * elem_size(f, CLOUDSC_B200_FP64);
+    if (!is_live(f)) continue;
+    off[f] = lane_bytes;
+    lane_bytes += ((size_t)chunk_blocks * blk[f] + 255) / 256 * 256;
+  }
+
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  Pipe &pipe = g_pipes[dev & 63];
+  std::lock_guard<std::mutex> lk(pipe.mu);
+  {
+    cudaError_t e = pipe_reserve(pipe, nstreams, lane_bytes);
+    if (e != cudaSuccess) { pipe.release(); return cuda_fail(e, "run_host: pipeline resources"); }
+  }
+
   double kernel_ms = 0.0;
   size_t h2d = 0, d2h = 0;
-  cudaEvent_t w0 = nullptr, w1 = nullptr;
-  auto cleanup = [&]() {
-    for (auto &l : lanes) {
-      for (int f = 0; f < CLOUDSC_NFIELDS; ++f)
-        if (l.dev[f]) cudaFree(l.dev[f]);
-      if (l.k0) cudaEventDestroy(l.k0);
-      if (l.k1) cudaEventDestroy(l.k1);
-      if (l.stream) cudaStreamDestroy(l.stream);
-    }
-    if (w0) cudaEventDestroy(w0);
-    if (w1) cudaEventDestroy(w1);
-  };
+  /* on error: drain what is in flight, then report (the cached resources stay valid) */
 #define CUX(call)                                                    \
   do {                                                               \
     cudaError_t e_ = (call);                                         \
-    if (e_ != cudaSuccess) { rc = cuda_fail(e_, #call); cleanup(); return rc; } \
+    if (e_ != cudaSuccess) {                                         \
+      for (int i_ = 0; i_ < nstreams; ++i_) cudaStreamSynchronize(pipe.lanes[i_].stream); \
+      return cuda_fail(e_, #call);                                   \
+    }                                                                \
   } while (0)
 
-  CUX(cudaEventCreate(&w0));
-  CUX(cudaEventCreate(&w1));
-  for (auto &l : lanes) {
-    CUX(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-    CUX(cudaEventCreate(&l.k0));
-    CUX(cudaEventCreate(&l.k1));
-    for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
-      if (!is_live(f)) continue;
-      CUX(cudaMalloc(&l.dev[f], (size_t)chunk_blocks * rows_of(f, klev) * nproma * elem_size(f, CLOUDSC_B200_FP64)));
-    }
-  }
-  CUX(cudaEventRecord(w0, 0));
+  CUX(cudaEventRecord(pipe.w0, 0));
   for (int c = 0; c < nchunks; ++c) {
-    Lane &l = lanes[c % nstreams];
+    Lane &l = pipe.lanes[c % nstreams];
     const int b0 = c * chunk_blocks;
     const int nb = (b0 + chunk_blocks <= nblocks) ? chunk_blocks : nblocks - b0;
     if (l.used) {  /* harvest the kernel time of the chunk that used this lane before */
@@ -363,14 +434,13 @@ int cloudsc_b200_run_host(void *const host[CLOUDSC_NFIELDS], int ngptot, int npr
       CUX(cudaEventElapsedTime(&ms, l.k0, l.k1));
       kernel_ms += ms;
     }
+    FieldTable ft;
+    for (int f = 0; f < CLOUDSC_NFIELDS; ++f) ft.p[f] = is_live(f) ? l.arena + off[f] : nullptr;
     for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
       if (!is_in(f)) continue;
-      const size_t blk = rows_of(f, klev) * nproma * elem_size(f, CLOUDSC_B200_FP64);
-      CUX(cudaMemcpyAsync(l.dev[f], (const char *)host[f] + (size_t)b0 * blk, (size_t)nb * blk, cudaMemcpyHostToDevice, l.stream));
-      h2d += (size_t)nb * blk;
+      CUX(cudaMemcpyAsync(ft.p[f], (const char *)host[f] + (size_t)b0 * blk[f], (size_t)nb * blk[f], cudaMemcpyHostToDevice, l.stream));
+      h2d += (size_t)nb * blk[f];
     }
-    FieldTable ft;
-    for (int i = 0; i < CLOUDSC_NFIELDS; ++i) ft.p[i] = l.dev[i];
     long long cend = (long long)(b0 + nb) * nproma;
     if (cend > ngptot) cend = ngptot;
     LaunchGeom g{0, (int)(cend - (long long)b0 * nproma), nproma, klev};
@@ -379,13 +449,13 @@ int cloudsc_b200_run_host(void *const host[CLOUDSC_NFIELDS], int ngptot, int npr
     CUX(cudaEventRecord(l.k1, l.stream));
     for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
       if (!is_out(f)) continue;
-      const size_t blk = rows_of(f, klev) * nproma * elem_size(f, CLOUDSC_B200_FP64);
-      CUX(cudaMemcpyAsync((char *)host[f] + (size_t)b0 * blk, l.dev[f], (size_t)nb * blk, cudaMemcpyDeviceToHost, l.stream));
-      d2h += (size_t)nb * blk;
+      CUX(cudaMemcpyAsync((char *)host[f] + (size_t)b0 * blk[f], ft.p[f], (size_t)nb * blk[f], cudaMemcpyDeviceToHost, l.stream));
+      d2h += (size_t)nb * blk[f];
     }
     l.used = true;
   }
-  for (auto &l : lanes) {
+  for (int i = 0; i < nstreams; ++i) {
+    Lane &l = pipe.lanes[i];
     CUX(cudaStreamSynchronize(l.stream));
     if (l.used) {
       float ms = 0.f;
@@ -393,12 +463,11 @@ int cloudsc_b200_run_host(void *const host[CLOUDSC_NFIELDS], int ngptot, int npr
       kernel_ms += ms;
     }
   }
-  CUX(cudaEventRecord(w1, 0));
-  CUX(cudaEventSynchronize(w1));
+  CUX(cudaEventRecord(pipe.w1, 0));
+  CUX(cudaEventSynchronize(pipe.w1));
   float wall = 0.f;
-  CUX(cudaEventElapsedTime(&wall, w0, w1));
+  CUX(cudaEventElapsedTime(&wall, pipe.w0, pipe.w1));
   if (stats) { stats[0] = (double)h2d; stats[1] = (double)d2h; stats[2] = kernel_ms; stats[3] = wall; }
-  cleanup();
 #undef CUX
   return 0;
 }

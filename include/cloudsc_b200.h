@@ -133,6 +133,9 @@ int cloudsc_b200_kernel_info(int nproma, int precision, int out[8]);
  */
 int cloudsc_b200_run_host(void *const host_fields[CLOUDSC_NFIELDS], int ngptot, int nproma, int klev,
                           double ptsphy, int chunk_blocks, int nstreams, double stats[4]);
+/* run_host keeps its streams and device staging arenas between calls (allocation costs more than
+ * the copies); this frees them on every device */
+int cloudsc_b200_release_cache(void);
 
 /* ---- handle API: resident device state for a fixed geometry (one handle per GPU) --------- */
 typedef struct cloudsc_b200_state cloudsc_b200_state;
