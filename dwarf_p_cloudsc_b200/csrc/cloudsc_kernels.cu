@@ -158,6 +158,18 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                : "memory");
 }
 
+/* one lane of a converged warp (elect.sync): lets ptxas issue the guarded uniform-datapath code once
+ * instead of wrapping every bulk copy in a "for each distinct active lane" loop */
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 /* 1 for the input slots whose row k+1 is staged with level k */
 __host__ __device__ constexpr int in_next(int s) { return (s == IN_PAPH || s == IN_PMFU || s == IN_PMFD || s == IN_PLU) ? 1 : 0; }
 
@@ -202,9 +214,12 @@ struct TileIO {
   __device__ __forceinline__ void level_end(int k) {
     __syncwarp();               /* every lane of this warp is done reading stage k&1 */
     if (WARPS > 1 && (threadIdx.x & 31) == 0) mbar_arrive(bar0 + 16u + 8u * ((unsigned)k & 1u));
-    if (threadIdx.x == 0 && k + 2 < klev) {
-      if (WARPS > 1) mbar_wait(bar0 + 16u + 8u * ((unsigned)k & 1u), ((unsigned)k >> 1) & 1u);
-      issue(k + 2);
+    if (k + 2 < klev && (WARPS == 1 || threadIdx.x < 32)) {   /* warp-uniform: the whole warp 0 enters */
+      if (elect_one()) {
+        if (WARPS > 1) mbar_wait(bar0 + 16u + 8u * ((unsigned)k & 1u), ((unsigned)k >> 1) & 1u);
+        issue(k + 2);
+      }
+      __syncwarp();
     }
   }
   template <int S> __device__ __forceinline__ T ld(int) const { return cur[S * kCols]; }
@@ -249,9 +264,12 @@ cloudsc_sweep_tile(const __grid_constant__ FieldTable ft, const LaunchGeom g, co
     mbar_fence_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    io.issue(0);
-    if (g.klev > 1) io.issue(1);
+  if (WARPS == 1 || threadIdx.x < 32) {
+    if (elect_one()) {
+      io.issue(0);
+      if (g.klev > 1) io.issue(1);
+    }
+    __syncwarp();
   }
   cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
 }
