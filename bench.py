@@ -40,6 +40,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+# stdout at the first collective), so file descriptor 1 is pointed at stderr for the whole run and the
+# result line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -153,13 +173,13 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args, rank, local_rank, world):
     import numpy as np
     import torch
-    from dwarf_p_cloudsc_b200 import api, params, state, validate
+    from dwarf_p_cloudsc_b200 import api, params, shard, state, validate
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the CLOUDSC hot path has no CPU fallback)")
@@ -181,7 +201,8 @@ def run_b200(args, rank, local_rank, world):
 
     # -- this rank's shard: global columns [rank*ngptot, (rank+1)*ngptot)  
     t_setup = time.time()
-    F = state.blocked_fields(cols, ngptot, nproma, klev, first_column=rank * ngptot)
+    first_column, _ = shard.weak_shard(rank, world, ngptot)
+    F = state.blocked_fields(cols, ngptot, nproma, klev, first_column=first_column)
     H = {n: torch.from_numpy(a).pin_memory() for n, a in F.items()}     # pinned host copies (e2e inputs)
     del F
     D = {n: t.to(dev, non_blocking=True) for n, t in H.items()}
@@ -217,10 +238,7 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
     times_ms = [a.elapsed_time(b) for a, b in ev]
     ms = sum(times_ms) / len(times_ms)
-    if dist:
-        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    ms = shard.reduce_max(ms, dist, dev)          # time = max over ranks; no collective on the data path
 
     # -- correctness of what was just timed: first 100 columns of rank 0 vs reference.h5
     ok = None
@@ -248,10 +266,7 @@ def run_b200(args, rank, local_rank, world):
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
             h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
         e2e_t = sum(e2e_ms) / len(e2e_ms)
-        if dist:
-            tt = torch.tensor([e2e_t], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_t = float(tt.item())
+        e2e_t = shard.reduce_max(e2e_t, dist, dev)
         e2e = {"value": world * ngptot / (e2e_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_t, "steps": e2e_steps,
                "api": "cloudsc_b200_run_host (C ABI, pinned host fields, chunked multi-stream H2D|kernel|D2H)"}
@@ -296,7 +311,7 @@ def run_b200(args, rank, local_rank, world):
         "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "validated_vs_reference_h5": ok, "step_ms": times_ms, "kernel_info": api.kernel_info(nproma),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist:
         dist.destroy_process_group()
 
@@ -318,6 +333,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (world == 1 and args.gpus > 1 and args.impl == "b200"):   # (the re-launching parent must pass stdout through)
+        capture_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
