@@ -105,14 +105,15 @@ static inline float cs(float x, float y) { return std::copysign(x, y); }
 
 /* ---- fast-mode primitives -------------------------------------------------------------------- */
 /*
- * exp(x) without the library's special-case handling: x is clamped to [-700, 700] (every call
- * site of the scheme is far inside; exp(-x^2) of the snow autoconversion underflows harmlessly to
- * 1e-304 instead of 0), n = rint(x*log2 e), r = x - n ln2 (two-constant Cody-Waite), degree-12
- * polynomial on |r| <= ln2/2 (fitted in extended precision, max rel. error 1.5e-16), scaling by
- * adding n to the exponent field.  ~22 instructions instead of ~66.
+ * exp(x) without the library's special-case handling, for |x| <= 700: n = rint(x*log2 e),
+ * r = x - n ln2 (two-constant Cody-Waite), degree-12 polynomial on |r| <= ln2/2 (fitted in extended
+ * precision, max rel. error 1.5e-16), scaling by adding n to the exponent field.  ~24 instructions
+ * instead of ~66.  Call sites whose argument is bounded by the physics (saturation formulae with
+ * 160 K <= T, nucleation, linear functions of T - RTT) use it directly; exp_fast_lo() clamps from
+ * below for the two that can run away to -inf (exp(-x^2) of the snow autoconversion, and pow_fast of
+ * a vanishing base), where the result underflows harmlessly to 1e-304 instead of 0.
  */
 CLOUDSC_FN double exp_fast(double x) {
-  x = mn(mx(x, -700.0), 700.0);
   const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
   const double t = x * 1.4426950408889634 + magic;
   const double fn = t - magic;
@@ -146,6 +147,8 @@ CLOUDSC_FN double exp_fast(double x) {
 #endif
 }
 CLOUDSC_FN float exp_fast(float x) { return ex_lib(x); }
+CLOUDSC_FN double exp_fast_lo(double x) { return exp_fast(mx(x, -700.0)); }
+CLOUDSC_FN float exp_fast_lo(float x) { return ex_lib(x); }
 
 /* 1/x by the hardware seed (MUFU.RCP64H, ~2^-20) + one cubically convergent step
  * r(1 + e + e^2), e = 1 - x r  (error e^3 ~ 2^-60), no zero/inf/denormal path (every divisor of the
@@ -203,7 +206,7 @@ CLOUDSC_FN double log_fast(double x) {
 }
 /* x^y for x > 0 as exp(y log x): relative error ~ |y log x| * 2e-16 (library pow: 0.5 ulp at ~15x the
  * instructions and a call into a spilling slow path).  exp_fast is declared above. */
-CLOUDSC_FN double pow_fast(double x, double y) { return exp_fast(y * log_fast(x)); }
+CLOUDSC_FN double pow_fast(double x, double y) { return exp_fast_lo(y * log_fast(x)); }
 CLOUDSC_FN float pow_fast(float x, float y) { return pw(x, y); }
 /* sqrt(x) for normal x > 0: MUFU.RSQ64H seed, two Newton steps on 1/sqrt, one on the root */
 CLOUDSC_FN double sqrt_fast(double x) {
@@ -234,6 +237,7 @@ template <typename T> CLOUDSC_FN T cube(T x) { return pw(x, T(3.0)); }
 #define CLOUDSC_POW15(x) pow15<T>(x)
 #define CLOUDSC_CUBE(x) cube<T>(x)
 template <typename T> CLOUDSC_FN T ex(T x) { return ex_lib(x); }
+template <typename T> CLOUDSC_FN T ex_lo(T x) { return ex_lib(x); }
 #else
 #define CLOUDSC_RCP(x) rcp_fast(x)
 #define CLOUDSC_DIV(a, b) ((a) * rcp_fast(b))
@@ -245,6 +249,7 @@ template <typename T> CLOUDSC_FN T cube(T x) { return (x * x) * x; }
 #define CLOUDSC_POW15(x) pow15<T>(x)
 #define CLOUDSC_CUBE(x) cube<T>(x)
 template <typename T> CLOUDSC_FN T ex(T x) { return exp_fast(x); }
+template <typename T> CLOUDSC_FN T ex_lo(T x) { return exp_fast_lo(x); }
 #endif
 
 /* State carried from level k-1 to level k (what "k-caching" keeps in registers) */
@@ -418,13 +423,11 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T cor_m = CLOUDSC_RCP(one - c.retv * foeewmt);
       const T qsmix = CLOUDSC_DIVR(foeewmt, one - c.retv * foeewmt, cor_m);
       const T zalfa = mx(zero, cs(one, t - c.rtt));
-      T foeew = mn(CLOUDSC_DIVR(zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice), pap, r_pap), T(0.5));
-      foeew = mn(T(0.5), foeew);
+      /* (the reference applies min(0.5, .) twice here; the second one is the identity) */
+      const T foeew = mn(CLOUDSC_DIVR(zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice), pap, r_pap), T(0.5));
       const T cor_i = CLOUDSC_RCP(one - c.retv * foeew);
       const T qsice = CLOUDSC_DIVR(foeew, one - c.retv * foeew, cor_i);
-      const T foeeliqt = mn(CLOUDSC_DIVR(c.r2es * e_liq, pap, r_pap), T(0.5));
-      const T cor_l = CLOUDSC_RCP(one - c.retv * foeeliqt);
-      const T qsliq = CLOUDSC_DIVR(foeeliqt, one - c.retv * foeeliqt, cor_l);
+      /* zqsliq (:607-609) is only read by the rain-evaporation block and is evaluated there */
       /* liquid/ice fractions, :628-636 */
       const T li = qx[0] + qx[1];
       T liqfrac = zero, icefrac = zero;
@@ -475,7 +478,6 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T dqsmixdt = (facm * cor_m) * qsmix;
       const T corqsmix = one + foeldcpm(c, alfa_w) * dqsmixdt;
       const T evaplimmix = mx(CLOUDSC_DIV(qsmix - qv, corqsmix), zero);
-      (void)cor_l;
       /* in-cloud condensate, :837-840 */
       const T tmpa = CLOUDSC_RCP(mx(a, c.zepsec));
       T liqcld = qx[0] * tmpa;
@@ -729,7 +731,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         if (icecld > c.zepsec) {
           const T zco = sc.snowlin * ex(c.rsnowlin2 * (t - c.rtt));
           const T x = CLOUDSC_DIVR(icecld, c.rlcritsnow, c.r_rlcritsnow);
-          const T snowaut = zco * (one - ex(-(x * x)));
+          const T snowaut = zco * (one - ex_lo(-(x * x)));
           qb13 = qb13 + snowaut;
         }
       }
@@ -823,8 +825,17 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       zzrh0 = mn(mx(zzrh0, c.rprecrhmax), one);
       {
         const T zzrh = mn(c.p08, zzrh0);
-        const T qe = mx(zero, mn(qv, qsliq));
-        if (covpclr > c.zepsec && qxfg[2] > c.zepsec && qe < zzrh * qsliq) {
+        bool rain_evap = covpclr > c.zepsec && qxfg[2] > c.zepsec;
+        T qsliq = zero, qe = zero;
+        if (rain_evap) {
+          const T foeeliqt = mn(CLOUDSC_DIVR(c.r2es * e_liq, pap, r_pap), T(0.5));   /* :607-609 */
+          const T cor_l = CLOUDSC_RCP(one - c.retv * foeeliqt);
+          (void)cor_l;
+          qsliq = CLOUDSC_DIVR(foeeliqt, one - c.retv * foeeliqt, cor_l);
+          qe = mx(zero, mn(qv, qsliq));
+          rain_evap = qe < zzrh * qsliq;
+        }
+        if (rain_evap) {
           const T preclr = CLOUDSC_DIV(qxfg[2], s.covptot);
           const T fallcorr = CLOUDSC_POW(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
           const T esatliq = sc.rv_rd * (c.r2es * e_liq);

@@ -188,7 +188,11 @@ struct TileIO {
   /* per thread */
   const T *stage_t;                   /* generic pointer: stage 0 + tid */
   const T *cur;                       /* stage of the level being processed + tid */
-  long long offL, offH, offC, off1;   /* element offsets of this thread's column (stores, scalars) */
+  long long offH, off1;               /* element offsets of this thread's column: paph rows, per-column scalars */
+  /* 32-bit element offsets of the CURRENT level's output rows (launcher guarantees every field has
+     fewer than 2^32 elements): base + offset is one IMAD.WIDE.U32 per store.  cH1 is row k+1 of the
+     [klev+1] flux fields, which is what level k writes. */
+  unsigned cL, cH1, cC, spstride;
 
   __device__ __forceinline__ void issue(int level) {   /* thread 0 only */
     const unsigned st = (unsigned)level & 1u;
@@ -221,19 +225,21 @@ struct TileIO {
       }
       __syncwarp();
     }
+    cL += (unsigned)stride; cH1 += (unsigned)stride; cC += (unsigned)stride;
   }
   template <int S> __device__ __forceinline__ T ld(int) const { return cur[S * kCols]; }
   template <int S> __device__ __forceinline__ T ld_next(int) const { return cur[S * kCols]; }
   __device__ __forceinline__ T paph_row(int r) const {
     return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PAPH]) + offH + (long long)r * stride);
   }
-  template <int S> __device__ __forceinline__ void st(int k, T v) {
-    T *base = static_cast<T *>(ft.p[out_field(S)]);
-    const long long off = (out_kind(S) == 0 ? offL : out_kind(S) == 1 ? offH : offC + (long long)out_species(S) * klev * stride)
-                        + (long long)k * stride;
-    __stcs(base + off, v);
+  template <int S> __device__ __forceinline__ void st(int, T v) {
+    const unsigned off = out_kind(S) == 0 ? cL : out_kind(S) == 1 ? cH1 : cC + (unsigned)out_species(S) * spstride;
+    __stcs(static_cast<T *>(ft.p[out_field(S)]) + off, v);
   }
-  template <int S> __device__ __forceinline__ void st_row0(T v) { st<S>(0, v); }
+  /* row 0 of a flux field, before the level loop (cH1 still points at row 1) */
+  template <int S> __device__ __forceinline__ void st_row0(T v) {
+    __stcs(static_cast<T *>(ft.p[out_field(S)]) + (cH1 - (unsigned)stride), v);
+  }
   __device__ __forceinline__ T plsm() const { return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PLSM]) + off1); }
   __device__ __forceinline__ int ktype() const { return __ldg(static_cast<const int *>(ft.p[CLOUDSC_F_KTYPE]) + off1); }
   __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
@@ -255,7 +261,8 @@ cloudsc_sweep_tile(const __grid_constant__ FieldTable ft, const LaunchGeom g, co
   IO io{ft, bL + jl0, bH + jl0, bL * 5 + jl0, g.nproma, g.klev,
         smem_u32(smem_raw), smem_u32(smem_raw + 2 * IO::kStage),
         reinterpret_cast<const T *>(smem_raw) + threadIdx.x,
-        nullptr, bL + jl, bH + jl, bL * 5 + jl, (long long)ibl * g.nproma + jl};
+        nullptr, bH + jl, (long long)ibl * g.nproma + jl,
+        (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma)};
   if (threadIdx.x == 0) {
     mbar_init(io.bar0, 1);
     mbar_init(io.bar0 + 8, 1);
@@ -494,6 +501,9 @@ const void *tile_fn(TileCfg cfg, size_t *smem) {
 template <typename T>
 bool tile_ok(const FieldTable &ft, const LaunchGeom &g, TileCfg cfg) {
   if (cfg.warps == 0 || g.col_begin % (32 * cfg.warps) != 0) return false;
+  /* the kernel addresses output rows with 32-bit element offsets */
+  const long long nblk = (g.col_end + g.nproma - 1) / g.nproma;
+  if (nblk * 5 * (g.klev + 1) * g.nproma >= (1ll << 32)) return false;
   for (int s = 0; s < N_IN; ++s)
     if (reinterpret_cast<uintptr_t>(ft.p[in_field(s)]) % 16 != 0) return false;
   return true;
