@@ -120,6 +120,10 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_name(ngptot, nproma, klev, precision):
+    return f"CLOUDSC {precision.upper()} NGPTOT={ngptot} per GPU, NPROMA={nproma}, KLEV={klev}, 100 reference columns replicated"
+
+
 def cpu_arm(ngptot_target, seconds_target=12.0, nthreads=0):
     """Time the CPU checker (reference build if present, else the port) on a bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -166,7 +170,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (100 reference columns replicated)",
-        "config": {"workload": f"dwarf-cloudsc-c NGPTOT={NGPTOT} NPROMA={NPROMA} KLEV={klev} FP64 (bounded sample on CPU)",
+        "config": {"workload": workload_name(NGPTOT, NPROMA, klev, "fp64"), "ngptot_per_gpu": NGPTOT, "nproma": NPROMA, "klev": klev,
+                   "reference_arm": f"dwarf-cloudsc-c kernel (unmodified cloudsc_c.c) on the host CPU, bounded sample of {n} columns per step, NPROMA={CPU_NPROMA}",
                    "sample_columns": n, "cpu_nproma": CPU_NPROMA},
         "gflops": 1e-9 * FLOP_PER_COLUMN * value,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": orc.kind, "sample": sample},
@@ -192,6 +197,8 @@ def run_b200(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
 
     ngptot, nproma = args.ngptot, args.nproma
+    fp32 = args.precision == "fp32"
+    prec = api.FP32 if fp32 else api.FP64
     cols, scalars, _, klev = state.load_input()
     p, k = params.params_from_scalars(scalars)
     pts = float(scalars["PTSPHY"])
@@ -206,6 +213,8 @@ def run_b200(args, rank, local_rank, world):
     H = {n: torch.from_numpy(a).pin_memory() for n, a in F.items()}     # pinned host copies (e2e inputs)
     del F
     D = {n: t.to(dev, non_blocking=True) for n, t in H.items()}
+    if fp32:                                                            # FP32 build: device fields are float (KTYPE stays int)
+        D = {n: (t.float() if t.dtype == torch.float64 else t) for n, t in D.items()}
     plude0 = D["PLUDE"].clone()
     torch.cuda.synchronize()
     tab = api.field_table(D)
@@ -213,7 +222,7 @@ def run_b200(args, rank, local_rank, world):
     log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s; kernel {api.kernel_info(nproma)}")
 
     def step():
-        api.launch_table(tab, ngptot, nproma, klev, pts, api.FP64, stream)
+        api.launch_table(tab, ngptot, nproma, klev, pts, prec, stream)
 
     for _ in range(args.warmup):
         D["PLUDE"].copy_(plude0)
@@ -244,15 +253,16 @@ def run_b200(args, rank, local_rank, world):
     ok = None
     if rank == 0:
         ref = state.load_reference()
-        errs = [validate.field_error(n, state.unblock(D[n][:1].cpu().numpy(), min(100, nproma))[..., :100],
-                                     ref[n][..., :min(100, nproma)], min(100, nproma)) for n in state.VALIDATE_ORDER]
-        ok = all(e.passes() for e in errs)
+        nv = min(100, nproma, ngptot)
+        errs = [validate.field_error(n, state.unblock(D[n][:1].double().cpu().numpy(), nv)[..., :nv],
+                                     ref[n][..., :nv], nv) for n in state.VALIDATE_ORDER]
+        ok = all(e.passes(args.precision) for e in errs)
         if not ok:
             log(validate.format_table(errs))
 
     # -- end to end through the public host API: pinned host buffers in, host buffers out
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not fp32:      # the host API is FP64 (the reference's field type)
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         plude_host0 = H["PLUDE"].clone()
         api.run_host(H, ngptot, nproma, klev, pts)            # warm-up (allocations, first touch)
@@ -276,7 +286,7 @@ def run_b200(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
-    bytes_col = params.algorithmic_bytes_per_column(klev)
+    bytes_col = params.algorithmic_bytes_per_column(klev, 4 if fp32 else 8)
     peak, peak_src = measured_peak_gbs()
     value = world * ngptot / (ms * 1e-3)
     achieved = bytes_col * ngptot / (ms * 1e-3) / 1e9         # per GPU, the dominant (only) kernel
@@ -301,15 +311,16 @@ def run_b200(args, rank, local_rank, world):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "metric": METRIC if not fp32 else METRIC.replace("fp64", "fp32"), "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if fp32 else "f64",
         "data": "synthetic (100 reference columns replicated to NGPTOT, g -> g mod 100)",
-        "config": {"workload": f"CLOUDSC FP64 NGPTOT={ngptot}/GPU NPROMA={nproma} KLEV={klev}, device-resident fields, one launch per step",
+        "config": {"workload": workload_name(ngptot, nproma, klev, args.precision), "residency": "device-resident fields, one launch per step",
                    "ngptot_per_gpu": ngptot, "nproma": nproma, "klev": klev, "parallelism": f"columns sharded x{world}, no collective",
-                   "l2": "inputs_exceed_l2 (9.2 GB of fields per step vs 126 MB L2)"},
+                   "l2": f"inputs_exceed_l2 ({bytes_col * ngptot / 1e9:.1f} GB of fields per step vs 126 MB L2)"},
         "gflops": 1e-9 * params.FLOP_PER_COLUMN * value,
         "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "validated_vs_reference_h5": ok, "step_ms": times_ms, "kernel_info": api.kernel_info(nproma),
+        "validated_vs_reference_h5": ok, "step_ms": times_ms, "kernel_info": api.kernel_info(nproma, prec),
     }
     emit(line)
     if dist:
@@ -325,6 +336,7 @@ def main():
     ap.add_argument("--ngptot", type=int, default=NGPTOT, help="columns per GPU")
     ap.add_argument("--nproma", type=int, default=NPROMA)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"], help="fp32 = the single-precision build (BASELINE configs[4])")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel sweeps only)")

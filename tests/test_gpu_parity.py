@@ -206,3 +206,31 @@ def test_c_driver_executable_validates_against_reference_h5(built, args):
     rows = [l for l in r.stdout.splitlines() if " 2D" in l]
     assert len(rows) == 21 and all(l.rstrip().endswith("PASS") for l in rows), r.stdout
     assert "TOTAL" in r.stdout and f"NGPTOT={args[1]}, NPROMA={args[2]}" in r.stdout
+
+
+@pytest.mark.parametrize("kernel_variant", [0, 2])
+def test_fp32_build_within_the_stated_single_precision_bars(built, oracle, input_data, kernel_variant):
+    """BASELINE configs[4]: the FP32 build (float device fields, float arithmetic) against the FP64 oracle,
+    per-field bars of validate.FP32_L1_BARS; every value finite."""
+    import torch
+    from dwarf_p_cloudsc_b200 import api, params, state, validate
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    ngptot, nproma = 1000, 128
+    F = state.blocked_fields(cols, ngptot, nproma, klev)
+    R = {n: a.copy() for n, a in F.items()}
+    oracle.run(R, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 0)
+    api.set_params(p, k)
+    D = {n: torch.from_numpy(a).cuda() for n, a in F.items()}
+    D = {n: (t.float() if t.dtype == torch.float64 else t) for n, t in D.items()}
+    try:
+        api.set_variant(kernel_variant)
+        api.launch(D, ngptot, nproma, klev, scalars["PTSPHY"], precision=api.FP32)
+        torch.cuda.synchronize()
+    finally:
+        api.set_variant(0)
+    G = {n: t.double().cpu().numpy() for n, t in D.items()}
+    for n in state.VALIDATE_ORDER:
+        assert np.isfinite(G[n]).all(), n
+    errs = validate.validate(G, R, ngptot)
+    assert validate.all_pass(errs, "fp32"), "\n" + validate.format_table(errs, "fp32")
