@@ -14,7 +14,8 @@ from typing import Dict, Mapping, Optional, Sequence
 from .params import FIELDS, NFIELDS, CloudscConsts, TECLDP
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcloudsc_b200.so")
+# $CLOUDSC_B200_LIB: an alternative build of the same library (compiler-flag experiments, tools/build_alt.sh)
+LIB_PATH = os.environ.get("CLOUDSC_B200_LIB") or os.path.join(_HERE, "lib", "libcloudsc_b200.so")
 
 FP64, FP32 = 0, 1
 VARIANT_AUTO, VARIANT_DIRECT, VARIANT_STAGED = 0, 1, 2

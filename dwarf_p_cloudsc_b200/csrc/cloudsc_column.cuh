@@ -54,6 +54,15 @@
 #define CLOUDSC_FN static inline
 #endif
 
+/* Code-layout hint only: blocks a minority of grid points reach (warm-phase and precipitation
+ * processes, detrainment, prescribed supersaturation) are moved out of the fall-through path, so the
+ * common path is fetched sequentially (the level body is ~3x the 32 KB instruction cache). */
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define CLOUDSC_RARE(x) __builtin_expect(!!(x), 0)
+#else
+#define CLOUDSC_RARE(x) (x)
+#endif
+
 namespace cloudsc {
 
 /* ---- input / output slots the IO policy understands ----------------------------------------- */
@@ -505,13 +514,13 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           const T qp1env = CLOUDSC_DIV(qv - a * qsice, mx(one_m_a, c.zepsilon));
           supsat = mx(CLOUDSC_DIVR(one_m_a * (qp1env - fac * qsice), corqsice, r_corqsice), zero);
         }
-        if (supsat > c.zepsec) {
+        if (CLOUDSC_RARE(supsat > c.zepsec)) {
           if (t > c.rthomo) { a04 = a04 - supsat; qxfg[0] = qxfg[0] + supsat; }
           else              { a14 = a14 - supsat; qxfg[1] = qxfg[1] + supsat; }
           solac = one_m_a * facI;
         }
         const T psupsat = io.template ld<IN_PSUPSAT>(k);
-        if (psupsat > c.zepsec) {
+        if (CLOUDSC_RARE(psupsat > c.zepsec)) {
           if (t > c.rthomo) { d0 = d0 + psupsat; psupsrce0 = psupsat; qxfg[0] = qxfg[0] + psupsat; }
           else              { d1 = d1 + psupsat; psupsrce1 = psupsat; qxfg[1] = qxfg[1] + psupsat; }
           solac = one_m_a * facI;
@@ -522,7 +531,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       if (k + 1 < klev) {
         const T plu_n = io.template ld_next<IN_PLU>(k);
         plude_out = plude_out * dtgdp;
-        if (plu_n > c.zepsec && plude_out > c.rlmin) {
+        if (CLOUDSC_RARE(plu_n > c.zepsec && plude_out > c.rlmin)) {
           solac = solac + CLOUDSC_DIV(plude_out, plu_n);
           convsrce0 = alfa_w * plude_out;
           convsrce1 = (one - alfa_w) * plude_out;
@@ -738,7 +747,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* 4.3b warm-rain autoconversion + accretion, Khairoutdinov-Kogan, :1644-1759 */
       if (liqcld > c.zepsec) {
         T rainaut, rainacc;
-        if (liqcld > lcrit_kk) {
+        if (CLOUDSC_RARE(liqcld > lcrit_kk)) {
           rainaut = ((((T(1.5) * a) * ptsphy) * c.rcl_kkaau) * CLOUDSC_POW(liqcld, c.rcl_kkbauq)) * kk_num_pow;
           rainaut = mn(rainaut, qxfg[0]);
           if (rainaut < c.zepsec) rainaut = zero;
@@ -756,7 +765,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       }
       /* riming of snow by cloud water, :1771-1785 */
       if (t <= c.rtt && liqcld > c.zepsec) {
-        if (s.covptot > c.p001 && snowcld > c.zepsec) {
+        if (CLOUDSC_RARE(s.covptot > c.p001 && snowcld > c.zepsec)) {
           const T fallcorr = CLOUDSC_POW(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
           T snowrime = ((((c.p03 * s.covptot) * ptsphy) * c.rcl_const7s) * fallcorr) *
                        CLOUDSC_POW((rho * snowcld) * c.rcl_const1s, c.rcl_const8s);
@@ -769,13 +778,13 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       {
         const T icetot = qxfg[1] + qxfg[3];
         T meltmax = zero;
-        if (icetot > c.zepsec && t > c.rtt) {
+        if (CLOUDSC_RARE(icetot > c.zepsec && t > c.rtt)) {
           const T subsat = mx(qsice - qv, zero);
           const T tdmtw0 = t - c.rtt - subsat * (c.ztw1 + c.ztw2 * (pap - ztw3) - c.ztw4 * (t - ztw5));
           const T cons1 = ab(CLOUDSC_DIVR(ptsphy * (one + T(0.5) * tdmtw0), c.rtaumel, c.r_rtaumel));
           meltmax = mx((tdmtw0 * cons1) * sc.zrldcp, zero);
         }
-        if (icetot > c.zepsec && meltmax > c.zepsec) {
+        if (CLOUDSC_RARE(icetot > c.zepsec && meltmax > c.zepsec)) {
           const T r_icetot = CLOUDSC_RCP(icetot);
           (void)r_icetot;
           T alfa = CLOUDSC_DIVR(qxfg[1], icetot, r_icetot);
@@ -789,7 +798,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         }
       }
       /* 4.4b freezing of rain, :1866-1906 */
-      if (qx[2] > c.zepsec) {
+      if (CLOUDSC_RARE(qx[2] > c.zepsec)) {
         if (t <= c.rtt && s.tp1_m1 > c.rtt) {
           const T qpre = mx(qx[3] + qx[2], c.zepsec);
           s.rainfrac = CLOUDSC_DIV(qx[2], qpre);
@@ -814,7 +823,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* 4.4c freezing of liquid, :1913-1928 */
       {
         const T frzmax = mx((c.rthomo - t) * sc.zrldcp, zero);
-        if (frzmax > c.zepsec && qxfg[0] > c.zepsec) {
+        if (CLOUDSC_RARE(frzmax > c.zepsec && qxfg[0] > c.zepsec)) {
           const T frz = mn(qxfg[0], frzmax);
           a01 = a01 + frz;
         }
@@ -827,7 +836,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         const T zzrh = mn(c.p08, zzrh0);
         bool rain_evap = covpclr > c.zepsec && qxfg[2] > c.zepsec;
         T qsliq = zero, qe = zero;
-        if (rain_evap) {
+        if (CLOUDSC_RARE(rain_evap)) {
           const T foeeliqt = mn(CLOUDSC_DIVR(c.r2es * e_liq, pap, r_pap), T(0.5));   /* :607-609 */
           const T cor_l = CLOUDSC_RCP(one - c.retv * foeeliqt);
           (void)cor_l;
@@ -835,7 +844,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           qe = mx(zero, mn(qv, qsliq));
           rain_evap = qe < zzrh * qsliq;
         }
-        if (rain_evap) {
+        if (CLOUDSC_RARE(rain_evap)) {
           const T preclr = CLOUDSC_DIV(qxfg[2], s.covptot);
           const T fallcorr = CLOUDSC_POW(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
           const T esatliq = sc.rv_rd * (c.r2es * e_liq);
@@ -901,27 +910,27 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 #define CLOUDSC_SCALE_D(d) if ((d) < zero) (d) = ((d) * ratio) * ratio
       {
         T mm = mx(qx[0], c.zepsec), sinksum = zero - (CLOUDSC_COLSUM0);
-        if (sinksum > mm) {
+        if (CLOUDSC_RARE(sinksum > mm)) {
           const T ratio = CLOUDSC_DIV(mm, sinksum);
           CLOUDSC_SCALE_D(d0); CLOUDSC_SCALE_HI(a01); CLOUDSC_SCALE_HI(a02); CLOUDSC_SCALE_HI(a03); CLOUDSC_SCALE_HI(a04);
         }
         mm = mx(qx[1], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM1);
-        if (sinksum > mm) {
+        if (CLOUDSC_RARE(sinksum > mm)) {
           const T ratio = CLOUDSC_DIV(mm, sinksum);
           CLOUDSC_SCALE_LO(a01); CLOUDSC_SCALE_D(d1); CLOUDSC_SCALE_HI(a12); CLOUDSC_SCALE_HI(a14);
         }
         mm = mx(qx[2], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM2);
-        if (sinksum > mm) {
+        if (CLOUDSC_RARE(sinksum > mm)) {
           const T ratio = CLOUDSC_DIV(mm, sinksum);
           CLOUDSC_SCALE_LO(a02); CLOUDSC_SCALE_LO(a12); CLOUDSC_SCALE_D(d2); CLOUDSC_SCALE_HI(a23); CLOUDSC_SCALE_HI(a24);
         }
         mm = mx(qx[3], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM3);
-        if (sinksum > mm) {
+        if (CLOUDSC_RARE(sinksum > mm)) {
           const T ratio = CLOUDSC_DIV(mm, sinksum);
           CLOUDSC_SCALE_LO(a03); CLOUDSC_SCALE_LO(a23); CLOUDSC_SCALE_D(d3); CLOUDSC_SCALE_HI(a34);
         }
         mm = mx(qv, c.zepsec); sinksum = zero - (CLOUDSC_COLSUM4);
-        if (sinksum > mm) {
+        if (CLOUDSC_RARE(sinksum > mm)) {
           const T ratio = CLOUDSC_DIV(mm, sinksum);
           CLOUDSC_SCALE_LO(a04); CLOUDSC_SCALE_LO(a14); CLOUDSC_SCALE_LO(a24); CLOUDSC_SCALE_LO(a34);
         }

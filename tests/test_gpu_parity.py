@@ -234,3 +234,65 @@ def test_fp32_build_within_the_stated_single_precision_bars(built, oracle, input
         assert np.isfinite(G[n]).all(), n
     errs = validate.validate(G, R, ngptot)
     assert validate.all_pass(errs, "fp32"), "\n" + validate.format_table(errs, "fp32")
+
+
+@pytest.mark.parametrize("kernel_variant", [0, 2, 5, 8, 9])
+def test_no_write_outside_the_fields(built, input_data, kernel_variant):
+    """Guard zones around every device field (compute-sanitizer is not available on the pool): 4 KB of a
+    canary pattern before and after each field must survive a launch on ragged geometries, and input
+    fields must come back unchanged (PLUDE is the only in/out field)."""
+    import torch
+    from dwarf_p_cloudsc_b200 import api, params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    api.set_params(p, k)
+    guard = 512                                    # elements of 8 bytes
+    canary = -1.2345678e300
+    try:
+        api.set_variant(kernel_variant)
+        for ngptot, nproma in ((257, 32), (300, 128), (77, 16), (1221, 64)):
+            F = state.blocked_fields(cols, ngptot, nproma, klev)
+            D, arenas = {}, {}
+            for n, a in F.items():
+                flat = torch.from_numpy(a.reshape(-1).view(np.float64 if a.dtype == np.float64 else np.int32))
+                if a.dtype == np.int32:             # KTYPE: int field, pad in int32 units
+                    ar = torch.full((flat.numel() + 4 * guard,), 0x7f7f7f7f, dtype=torch.int32, device="cuda")
+                    ar[2 * guard:2 * guard + flat.numel()] = flat.cuda()
+                    D[n] = ar[2 * guard:2 * guard + flat.numel()]
+                else:
+                    ar = torch.full((flat.numel() + 2 * guard,), canary, dtype=torch.float64, device="cuda")
+                    ar[guard:guard + flat.numel()] = flat.cuda()
+                    D[n] = ar[guard:guard + flat.numel()]
+                arenas[n] = ar
+            api.launch(D, ngptot, nproma, klev, scalars["PTSPHY"])
+            torch.cuda.synchronize()
+            for n, ar in arenas.items():
+                if ar.dtype == torch.int32:
+                    assert bool((ar[:2 * guard] == 0x7f7f7f7f).all()) and bool((ar[-2 * guard:] == 0x7f7f7f7f).all()), n
+                else:
+                    assert bool((ar[:guard] == canary).all()) and bool((ar[-guard:] == canary).all()), (n, ngptot, nproma)
+            for f in params.INPUT_FIELDS:
+                if f.use == "R" and f.name in F:
+                    assert np.array_equal(D[f.name].cpu().numpy().view(F[f.name].dtype).reshape(F[f.name].shape), F[f.name]), f.name
+    finally:
+        api.set_variant(0)
+
+
+def test_columns_are_independent(built, input_data):
+    """Permuting the source columns permutes the outputs bit for bit: no value leaks between the columns
+    of a warp / CTA through the shared-memory staging."""
+    import torch
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(100)
+    c2 = {n: np.ascontiguousarray(a[..., perm]) for n, a in cols.items()}
+    ngptot, nproma = 1000, 128
+    G1 = _run_gpu(state.blocked_fields(cols, ngptot, nproma, klev), p, k, ngptot, nproma, klev, scalars["PTSPHY"])
+    G2 = _run_gpu(state.blocked_fields(c2, ngptot, nproma, klev), p, k, ngptot, nproma, klev, scalars["PTSPHY"])
+    idx = perm[np.arange(ngptot) % 100]            # column g of run 2 holds source column perm[g mod 100]
+    for f in params.OUTPUT_FIELDS:
+        u1 = state.unblock(G1[f.name], ngptot)[..., :100]
+        u2 = state.unblock(G2[f.name], ngptot)
+        assert np.array_equal(u2, u1[..., idx]), f.name
