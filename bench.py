@@ -70,8 +70,10 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the sampler runs from before
+    the warm-up (nvidia-smi needs ~0.1 s to deliver its first row) and only rows time-stamped inside
+    [mark_begin, mark_end] are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -79,11 +81,12 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -92,23 +95,44 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        import datetime
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = self.t0 or 0.0
+        t1 = self.t1 or time.time()
+
+        def stamp(row_time, text):
+            try:   # nvidia-smi's own clock (same host), e.g. 2026/10/18 12:34:56.789
+                return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                return row_time
+        parsed = []
+        for rt, r in self.rows:
             c = [x.strip() for x in r.split(",")]
-            if len(c) < 7:
+            if len(c) < 8:
                 continue
+            parsed.append((stamp(rt, c[0]), c[1:]))
+        inside = [c for ts, c in parsed if t0 <= ts <= t1 + 0.02]
+        if not inside:                       # very short region: the rows closest after its start
+            inside = [c for ts, c in parsed if ts >= t0][:2] or [c for _, c in parsed][-2:]
+        for c in inside:
             try:
                 sm.append(float(c[0])); mx.append(float(c[1])); pw.append(float(c[2]))
             except ValueError:
@@ -224,17 +248,18 @@ def run_b200(args, rank, local_rank, world):
     def step():
         api.launch_table(tab, ngptot, nproma, klev, pts, prec, stream)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         D["PLUDE"].copy_(plude0)
         step()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark_begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in ev:
         D["PLUDE"].copy_(plude0)          # restore the in/out field, outside the event pair
@@ -244,6 +269,7 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     times_ms = [a.elapsed_time(b) for a, b in ev]
     ms = sum(times_ms) / len(times_ms)
@@ -320,7 +346,8 @@ def run_b200(args, rank, local_rank, world):
                    "l2": f"inputs_exceed_l2 ({bytes_col * ngptot / 1e9:.1f} GB of fields per step vs 126 MB L2)"},
         "gflops": 1e-9 * params.FLOP_PER_COLUMN * value,
         "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "validated_vs_reference_h5": ok, "step_ms": times_ms, "kernel_info": api.kernel_info(nproma, prec),
+        "validated_vs_reference_h5": ok,
+        "step_ms": {"min": min(times_ms), "median": statistics.median(times_ms), "max": max(times_ms)}, "kernel_info": api.kernel_info(nproma, prec),
     }
     emit(line)
     if dist:
@@ -330,7 +357,7 @@ def run_b200(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ngptot", type=int, default=NGPTOT, help="columns per GPU")
