@@ -497,6 +497,26 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T r_1ma = CLOUDSC_RCP(mx(c.zepsec, one_m_a));
       (void)r_1ma;
 
+      /* ================= 3.4 condensation/evaporation due to dqsat/dT, :1137-1182 ========= */
+      /* (evaluated here, ahead of 3.1-3.4: it is a pure function of this level's inputs, and next to the
+       * saturation block its two Newton steps overlap with that block's exp/reciprocal chains) */
+      T dqs;
+      {
+        const T dtdp = CLOUDSC_DIVR(sc.zrdcp * t, pap, r_pap);
+        const T dpmxdt = dp * zqtmst;
+        const T mfdn = (k + 1 < klev) ? mf_n : zero;
+        T wtot = io.template ld<IN_PVERVEL>(k) + sc.half_rg * (s.mf_k + mfdn);
+        wtot = mn(dpmxdt, mx(-dpmxdt, wtot));
+        const T zzzdt = io.template ld<IN_PHRSW>(k) + io.template ld<IN_PHRLW>(k);
+        const T dtdiab = mn(dpmxdt * dtdp, mx(-dpmxdt * dtdp, zzzdt)) * ptsphy; /* + ralfdcp*zldefr, zldefr == 0 */
+        const T dtforc = (dtdp * wtot) * ptsphy + dtdiab;
+        T tn = t + dtforc;
+        tn = mx(tn, T(160.0));
+        T qsm = qsmix;
+        satadj_step(c, r_pap, tn, qsm);
+        satadj_step(c, r_pap, tn, qsm);
+        dqs = qsm - qsmix;
+      }
       /* evaporate very small amounts of liquid and ice, :847-857 */
       if (qx[0] < c.rlmin) a04 = qx[0];
       if (qx[1] < c.rlmin) a14 = qx[1];
@@ -592,24 +612,6 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         }
       }
 
-      /* ================= 3.4 condensation/evaporation due to dqsat/dT, :1137-1182 ========= */
-      T dqs;
-      {
-        const T dtdp = CLOUDSC_DIVR(sc.zrdcp * t, pap, r_pap);
-        const T dpmxdt = dp * zqtmst;
-        const T mfdn = (k + 1 < klev) ? mf_n : zero;
-        T wtot = io.template ld<IN_PVERVEL>(k) + sc.half_rg * (s.mf_k + mfdn);
-        wtot = mn(dpmxdt, mx(-dpmxdt, wtot));
-        const T zzzdt = io.template ld<IN_PHRSW>(k) + io.template ld<IN_PHRLW>(k);
-        const T dtdiab = mn(dpmxdt * dtdp, mx(-dpmxdt * dtdp, zzzdt)) * ptsphy; /* + ralfdcp*zldefr, zldefr == 0 */
-        const T dtforc = (dtdp * wtot) * ptsphy + dtdiab;
-        T tn = t + dtforc;
-        tn = mx(tn, T(160.0));
-        T qsm = qsmix;
-        satadj_step(c, r_pap, tn, qsm);
-        satadj_step(c, r_pap, tn, qsm);
-        dqs = qsm - qsmix;
-      }
       /* 3.4a evaporation of clouds, :1191-1205 */
       if (dqs > zero) {
         T levap = a * mn(dqs, licld);
@@ -908,32 +910,41 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 #define CLOUDSC_SCALE_LO(a) if ((a) < zero) (a) = (a) * ratio
 #define CLOUDSC_SCALE_HI(a) if ((a) > zero) (a) = (a) * ratio
 #define CLOUDSC_SCALE_D(d) if ((d) < zero) (d) = ((d) * ratio) * ratio
-      {
-        T mm = mx(qx[0], c.zepsec), sinksum = zero - (CLOUDSC_COLSUM0);
-        if (CLOUDSC_RARE(sinksum > mm)) {
-          const T ratio = CLOUDSC_DIV(mm, sinksum);
+      /* The five species are limited one after the other (a scaled pair feeds the later column sums),
+       * but when no column exceeds its content -- the common case -- nothing is scaled at all and the
+       * five unscaled sums are also the explicit sums of :2330.  So: all five sums and tests up front
+       * (independent chains), and the sequential pass only if one of them fires; by induction over m
+       * the pass cannot fire unless one of the up-front tests does. */
+      T cs0 = CLOUDSC_COLSUM0, cs1 = CLOUDSC_COLSUM1, cs2 = CLOUDSC_COLSUM2, cs3 = CLOUDSC_COLSUM3, cs4 = CLOUDSC_COLSUM4;
+      const T mm0 = mx(qx[0], c.zepsec), mm1 = mx(qx[1], c.zepsec), mm2 = mx(qx[2], c.zepsec), mm3 = mx(qx[3], c.zepsec),
+              mm4 = mx(qv, c.zepsec);
+      if (CLOUDSC_RARE((zero - cs0 > mm0) | (zero - cs1 > mm1) | (zero - cs2 > mm2) | (zero - cs3 > mm3) | (zero - cs4 > mm4))) {
+        T sinksum = zero - cs0;
+        if (sinksum > mm0) {
+          const T ratio = CLOUDSC_DIV(mm0, sinksum);
           CLOUDSC_SCALE_D(d0); CLOUDSC_SCALE_HI(a01); CLOUDSC_SCALE_HI(a02); CLOUDSC_SCALE_HI(a03); CLOUDSC_SCALE_HI(a04);
         }
-        mm = mx(qx[1], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM1);
-        if (CLOUDSC_RARE(sinksum > mm)) {
-          const T ratio = CLOUDSC_DIV(mm, sinksum);
+        sinksum = zero - (CLOUDSC_COLSUM1);
+        if (sinksum > mm1) {
+          const T ratio = CLOUDSC_DIV(mm1, sinksum);
           CLOUDSC_SCALE_LO(a01); CLOUDSC_SCALE_D(d1); CLOUDSC_SCALE_HI(a12); CLOUDSC_SCALE_HI(a14);
         }
-        mm = mx(qx[2], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM2);
-        if (CLOUDSC_RARE(sinksum > mm)) {
-          const T ratio = CLOUDSC_DIV(mm, sinksum);
+        sinksum = zero - (CLOUDSC_COLSUM2);
+        if (sinksum > mm2) {
+          const T ratio = CLOUDSC_DIV(mm2, sinksum);
           CLOUDSC_SCALE_LO(a02); CLOUDSC_SCALE_LO(a12); CLOUDSC_SCALE_D(d2); CLOUDSC_SCALE_HI(a23); CLOUDSC_SCALE_HI(a24);
         }
-        mm = mx(qx[3], c.zepsec); sinksum = zero - (CLOUDSC_COLSUM3);
-        if (CLOUDSC_RARE(sinksum > mm)) {
-          const T ratio = CLOUDSC_DIV(mm, sinksum);
+        sinksum = zero - (CLOUDSC_COLSUM3);
+        if (sinksum > mm3) {
+          const T ratio = CLOUDSC_DIV(mm3, sinksum);
           CLOUDSC_SCALE_LO(a03); CLOUDSC_SCALE_LO(a23); CLOUDSC_SCALE_D(d3); CLOUDSC_SCALE_HI(a34);
         }
-        mm = mx(qv, c.zepsec); sinksum = zero - (CLOUDSC_COLSUM4);
-        if (CLOUDSC_RARE(sinksum > mm)) {
-          const T ratio = CLOUDSC_DIV(mm, sinksum);
+        sinksum = zero - (CLOUDSC_COLSUM4);
+        if (sinksum > mm4) {
+          const T ratio = CLOUDSC_DIV(mm4, sinksum);
           CLOUDSC_SCALE_LO(a04); CLOUDSC_SCALE_LO(a14); CLOUDSC_SCALE_LO(a24); CLOUDSC_SCALE_LO(a34);
         }
+        cs0 = CLOUDSC_COLSUM0; cs1 = CLOUDSC_COLSUM1; cs2 = CLOUDSC_COLSUM2; cs3 = CLOUDSC_COLSUM3; cs4 = CLOUDSC_COLSUM4;
       }
 
       /* ================= 5.2.2 implicit solve, :2294-2397 ================================= */
@@ -945,11 +956,11 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
        * every diagonal unchanged, and the back-substitution is a plain divide per species.
        */
       T qxn[5];
-      qxn[0] = qx[0] + (CLOUDSC_COLSUM0);
-      qxn[1] = qx[1] + (CLOUDSC_COLSUM1);
-      qxn[2] = qx[2] + (CLOUDSC_COLSUM2);
-      qxn[3] = qx[3] + (CLOUDSC_COLSUM3);
-      qxn[4] = qv + (CLOUDSC_COLSUM4);
+      qxn[0] = qx[0] + cs0;
+      qxn[1] = qx[1] + cs1;
+      qxn[2] = qx[2] + cs2;
+      qxn[3] = qx[3] + cs3;
+      qxn[4] = qv + cs4;
 #undef CLOUDSC_COLSUM0
 #undef CLOUDSC_COLSUM1
 #undef CLOUDSC_COLSUM2
@@ -974,10 +985,12 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         qxn[1] = CLOUDSC_DIVR(qxn[1], den1, r_den1);
         qxn[0] = CLOUDSC_DIVR(qxn[0], den0, r_den0);
       }
-      /* clip small/negative values into vapour, :2402-2412 */
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        if (qxn[n] < c.zepsec) { qxn[4] = qxn[4] + qxn[n]; qxn[n] = zero; }
+      /* clip small/negative values into vapour, :2402-2412 -- as selects: the four tests are independent
+       * and qxn[v] + 0 == qxn[v] where the reference adds nothing */
+      {
+        const bool c0 = qxn[0] < c.zepsec, c1 = qxn[1] < c.zepsec, c2 = qxn[2] < c.zepsec, c3 = qxn[3] < c.zepsec;
+        qxn[4] = (((qxn[4] + (c0 ? qxn[0] : zero)) + (c1 ? qxn[1] : zero)) + (c2 ? qxn[2] : zero)) + (c3 ? qxn[3] : zero);
+        qxn[0] = c0 ? zero : qxn[0]; qxn[1] = c1 ? zero : qxn[1]; qxn[2] = c2 ? zero : qxn[2]; qxn[3] = c3 ? zero : qxn[3];
       }
       /* variables needed for next level, :2417-2423 */
       s.qlnm1 = qxn[0]; s.qinm1 = qxn[1];
