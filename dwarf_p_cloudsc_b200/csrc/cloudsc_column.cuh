@@ -298,14 +298,18 @@ CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
   const T ei = ex(CLOUDSC_DIVR(c.r3ies * (tn - c.rtt), di, rdi));
   T qsat = (c.r2es * (al * el + (one - al) * ei)) * qp;
   qsat = mn(T(0.5), qsat);
-  const T cor = CLOUDSC_RCP(one - c.retv * qsat);
-  qsat = qsat * cor;
 #if CLOUDSC_STRICT
+  const T cor = one / (one - c.retv * qsat);
+  qsat = qsat * cor;
   const T dem = (al * c.r5alvcp) * (one / (dl * dl)) + ((one - al) * c.r5alscp) * (one / (di * di)); /* FOEDEM */
+  const T cond = (qsm - qsat) / (one + (qsat * cor) * dem);
 #else
+  /* (qsm - u/d) / (1 + (u/d)(1/d) dem) with d = 1 - retv u  ==  (qsm d - u) d / (d^2 + u dem):
+     one reciprocal on the Newton step's critical path instead of two */
   const T dem = (al * c.r5alvcp) * (rdl * rdl) + ((one - al) * c.r5alscp) * (rdi * rdi);
+  const T d = one - c.retv * qsat;
+  const T cond = ((qsm * d - qsat) * d) * rcp_fast(d * d + qsat * dem);
 #endif
-  const T cond = CLOUDSC_DIV(qsm - qsat, one + (qsat * cor) * dem);
   tn = tn + foeldcpm(c, al) * cond;
   qsm = qsm - cond;
 }
@@ -381,29 +385,34 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
     for (int m = 0; m < 4; ++m) qx0[m] = qx[m];
     T tend_t = zero, tend_q = zero;
 
-    /* ---- tidy up very small cloud cover / condensate, :519-541 */
-    if (qx[0] + qx[1] < c.rlmin || a < c.ramin) {
-      T qadj = qx[0] * zqtmst;
+    /* ---- tidy up very small cloud cover / condensate, :519-541, and small CLV variables, :547-575
+     * (iphase = l:1 i:2 r:1 s:2).  Written as selects: where the reference does nothing, a zero is
+     * added (x + 0 == x), so the values are the reference's and the block is branch-free -- it shares
+     * one basic block with the saturation chains below, whose latencies it helps to fill. */
+    {
+      const bool clr = (qx[0] + qx[1] < c.rlmin) | (a < c.ramin);
+      T v = clr ? qx[0] : zero;
+      T qadj = v * zqtmst;
       tend_q = tend_q + qadj;
       tend_t = tend_t - c.ralvdcp * qadj;
-      qv = qv + qx[0];
-      qx[0] = zero;
-      qadj = qx[1] * zqtmst;
+      qv = qv + v;
+      qx[0] = clr ? zero : qx[0];
+      v = clr ? qx[1] : zero;
+      qadj = v * zqtmst;
       tend_q = tend_q + qadj;
       tend_t = tend_t - c.ralsdcp * qadj;
-      qv = qv + qx[1];
-      qx[1] = zero;
-      a = zero;
-    }
-    /* ---- tidy up small CLV variables, :547-575 (iphase = l:1 i:2 r:1 s:2) */
+      qv = qv + v;
+      qx[1] = clr ? zero : qx[1];
+      a = clr ? zero : a;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (qx[m] < c.rlmin) {
-        const T qadj = qx[m] * zqtmst;
+      for (int m = 0; m < 4; ++m) {
+        const bool small = qx[m] < c.rlmin;
+        v = small ? qx[m] : zero;
+        qadj = v * zqtmst;
         tend_q = tend_q + qadj;
         tend_t = tend_t - ((m & 1) ? c.ralsdcp : c.ralvdcp) * qadj;
-        qv = qv + qx[m];
-        qx[m] = zero;
+        qv = qv + v;
+        qx[m] = small ? zero : qx[m];
       }
     }
 
@@ -439,8 +448,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* zqsliq (:607-609) is only read by the rain-evaporation block and is evaluated there */
       /* liquid/ice fractions, :628-636 */
       const T li = qx[0] + qx[1];
-      T liqfrac = zero, icefrac = zero;
-      if (li > c.rlmin) { liqfrac = CLOUDSC_DIV(qx[0], li); icefrac = one - liqfrac; }
+      const bool has_li = li > c.rlmin;
+      const T liqfrac_u = CLOUDSC_DIV(qx[0], li);      /* discarded (possibly inf/nan) where li <= rlmin */
+      const T liqfrac = has_li ? liqfrac_u : zero;
+      const T icefrac = has_li ? one - liqfrac_u : zero;
 
       /* ================= 3.0 initialise, :739-859 ========================================= */
       T qxfg[4] = {qx[0], qx[1], qx[2], qx[3]};
@@ -518,8 +529,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         dqs = qsm - qsmix;
       }
       /* evaporate very small amounts of liquid and ice, :847-857 */
-      if (qx[0] < c.rlmin) a04 = qx[0];
-      if (qx[1] < c.rlmin) a14 = qx[1];
+      a04 = qx[0] < c.rlmin ? qx[0] : zero;
+      a14 = qx[1] < c.rlmin ? qx[1] : zero;
 
       /* ================= 3.1 ice supersaturation adjustment, :879-952 ===================== */
       const T fokoop = mn(c.rkoop1 - c.rkoop2 * t, CLOUDSC_DIV(c.r2es * e_liq, c.r2es * e_ice));
