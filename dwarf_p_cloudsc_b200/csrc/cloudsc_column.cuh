@@ -508,11 +508,33 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T r_1ma = CLOUDSC_RCP(mx(c.zepsec, one_m_a));
       (void)r_1ma;
 
+      const T fokoop = mn(c.rkoop1 - c.rkoop2 * t, CLOUDSC_DIV(c.r2es * e_liq, c.r2es * e_ice));
+      /* ---- does anything read zdqs at this point?  3.4a / 3.4b(1) act on existing cloud only (a > 0; with
+       * a == 0 they add zeros), 3.4b(2) only inside the humidity window below, which does not depend on
+       * zdqs.  Where neither holds -- every clear, dry point: the whole stratosphere -- the two Newton
+       * steps (4 exp, 6 reciprocals) are not evaluated at all.  Exact: zdqs is dead there. */
+      T rhc = c.ramid;
+      {
+        const T sigk = CLOUDSC_DIVR(pap, paph_surf, r_paph_surf);
+        if (sigk > c.p08) { const T x = CLOUDSC_DIVR(sigk - c.p08, c.p02, c.r_p02); rhc = c.ramid + sc.one_m_ramid * (x * x); }
+      }
+      T qe_nc;                                         /* zqe of :1275-1302 */
+      if (c.nssopt == 0 || c.nssopt == 1) {
+        qe_nc = CLOUDSC_DIVR(qv - a * qsice, mx(c.zepsec, one_m_a), r_1ma);
+        qe_nc = mx(zero, qe_nc);
+      } else if (c.nssopt == 2) {
+        qe_nc = qv;
+      } else {
+        qe_nc = qv + li;
+      }
+      const T fac_nc = (c.nssopt == 0 || t >= c.rtt) ? one : fokoop;
+      const bool new_cloud_window = a < sc.one_m_zepsec && qe_nc >= qsice * fac_nc * rhc && qe_nc < qsice * fac_nc;
+      const bool need_dqs = (a > zero) | new_cloud_window;
       /* ================= 3.4 condensation/evaporation due to dqsat/dT, :1137-1182 ========= */
       /* (evaluated here, ahead of 3.1-3.4: it is a pure function of this level's inputs, and next to the
        * saturation block its two Newton steps overlap with that block's exp/reciprocal chains) */
-      T dqs;
-      {
+      T dqs = zero;
+      if (need_dqs) {
         const T dtdp = CLOUDSC_DIVR(sc.zrdcp * t, pap, r_pap);
         const T dpmxdt = dp * zqtmst;
         const T mfdn = (k + 1 < klev) ? mf_n : zero;
@@ -533,7 +555,6 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       a14 = qx[1] < c.rlmin ? qx[1] : zero;
 
       /* ================= 3.1 ice supersaturation adjustment, :879-952 ===================== */
-      const T fokoop = mn(c.rkoop1 - c.rkoop2 * t, CLOUDSC_DIV(c.r2es * e_liq, c.r2es * e_ice));
       {
         T fac, facI;
         if (c.nssopt == 0 || t >= c.rtt) { fac = one; facI = one; }
@@ -653,21 +674,9 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         else              { a14 = a14 - lcond1; qxfg[1] = qxfg[1] + lcond1; }
       }
       /* 3.4b (2) generation of new clouds, :1254-1361 */
-      if (dqs <= -c.rlmin && a < sc.one_m_zepsec) {
-        T rhc = c.ramid;
-        const T sigk = CLOUDSC_DIVR(pap, paph_surf, r_paph_surf);
-        if (sigk > c.p08) { const T x = CLOUDSC_DIVR(sigk - c.p08, c.p02, c.r_p02); rhc = c.ramid + sc.one_m_ramid * (x * x); }
-        T qe;
-        if (c.nssopt == 0 || c.nssopt == 1) {
-          qe = CLOUDSC_DIVR(qv - a * qsice, mx(c.zepsec, one_m_a), r_1ma);
-          qe = mx(zero, qe);
-        } else if (c.nssopt == 2) {
-          qe = qv;
-        } else {
-          qe = qv + li;
-        }
-        const T fac = (c.nssopt == 0 || t >= c.rtt) ? one : fokoop;
-        if (qe >= qsice * fac * rhc && qe < qsice * fac) {
+      if (dqs <= -c.rlmin && new_cloud_window) {
+        const T qe = qe_nc, fac = fac_nc;
+        {
           T acond = CLOUDSC_DIV(-(one_m_a * fac) * dqs, mx(T(2.0) * (fac * qsice - qe), c.zepsec));
           acond = mn(acond, one_m_a);
           T lcond2 = (-(fac * dqs) * T(0.5)) * acond;
