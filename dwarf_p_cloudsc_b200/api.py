@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLOUDSC_B200_LIB") or os.path.join(_HERE, "lib", "libcloudsc_b200.so")
 
 FP64, FP32 = 0, 1
-VARIANT_AUTO, VARIANT_DIRECT, VARIANT_STAGED = 0, 1, 2
+VARIANT_AUTO = 0   # see csrc/cloudsc_kernels.cuh for the other kernel variants
 
 
 class CloudscError(RuntimeError):
@@ -63,6 +63,8 @@ lib.cloudsc_b200_field_ptr.restype = _vp
 lib.cloudsc_b200_field_ptr.argtypes = [_vp, _i]
 lib.cloudsc_b200_sync.argtypes = [_vp]
 lib.cloudsc_b200_set_variant.argtypes = [_i]
+lib.cloudsc_b200_state_kernel_info.argtypes = [_vp, ctypes.POINTER(ctypes.c_int * 8)]
+lib.cloudsc_b200_state_kernel_info.restype = _i
 lib.cloudsc_c.argtypes = [_i, _i, _i, _i, _d] + [_vp] * NFIELDS
 for _n in ("set_params", "launch", "kernel_info", "run_host", "create", "destroy", "upload", "download",
            "step", "reset_inout", "sync", "set_variant", "get_variant", "device_count",
@@ -176,6 +178,13 @@ class State:
 
     def reset_inout(self, stream: int = 0):
         _check(lib.cloudsc_b200_reset_inout(self._h, ctypes.c_void_p(stream)))
+
+    def kernel_info(self) -> Dict[str, int]:
+        out = (ctypes.c_int * 8)()
+        _check(lib.cloudsc_b200_state_kernel_info(self._h, ctypes.byref(out)))
+        keys = ("registers", "local_bytes", "static_smem", "max_threads_per_block", "blocks_per_sm",
+                "block_threads", "variant", "dynamic_smem")
+        return dict(zip(keys, out))
 
     def field_ptr(self, name: str) -> int:
         from .params import FIELD_INDEX

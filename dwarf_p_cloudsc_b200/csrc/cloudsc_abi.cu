@@ -209,10 +209,40 @@ int cloudsc_b200_sync(void *stream) {
 /* ---------------------------------------------------------------------------------------------- */
 struct cloudsc_b200_state {
   int ngptot, nproma, klev, nblocks, precision, device;
-  void *dev[CLOUDSC_NFIELDS];
-  void *plude0;  /* pristine copy of the in/out field */
+  void *dev[CLOUDSC_NFIELDS];   /* pointers into `arena` */
+  void *plude0;                 /* pristine copy of the in/out field */
   size_t bytes[CLOUDSC_NFIELDS];
+  char *arena;                  /* ONE allocation: fields of a kind at a constant spacing (see TensorMaps) */
+  TensorMaps tm;
+  bool has_tm;                  /* tensor maps encoded: step() uses the 4-requests-per-level TMA kernel */
 };
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+/* rank-R FP64 tensor map over `base`: dims/box innermost first, strides (bytes) of dims 1..R-1 */
+bool encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline size_t up256(size_t n) { return (n + 255) / 256 * 256; }
+}  // namespace
 
 int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc_b200_state **out) {
   if (!out) return fail(CLOUDSC_B200_EARG, "create: out is NULL");
@@ -224,22 +254,53 @@ int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc
   st->ngptot = ngptot; st->nproma = nproma; st->klev = klev; st->precision = precision;
   st->nblocks = (ngptot + nproma - 1) / nproma;
   cudaGetDevice(&st->device);
+
+  /* arena layout: the three tensor-map groups first, each with a constant field spacing, then the rest */
+  size_t off[CLOUDSC_NFIELDS];
+  bool placed[CLOUDSC_NFIELDS] = {false};
+  size_t total = 0;
   for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
-    if (!is_live(f)) continue;
-    st->bytes[f] = (size_t)st->nblocks * rows_of(f, klev) * nproma * elem_size(f, precision);
-    cudaError_t e = cudaMalloc(&st->dev[f], st->bytes[f]);
-    if (e != cudaSuccess) { cloudsc_b200_destroy(st); return cuda_fail(e, "cudaMalloc(field)"); }
+    off[f] = 0;
+    st->bytes[f] = is_live(f) ? (size_t)st->nblocks * rows_of(f, klev) * nproma * elem_size(f, precision) : 0;
   }
-  cudaError_t e = cudaMalloc(&st->plude0, st->bytes[CLOUDSC_F_PLUDE]);
+  auto place = [&](int f) { off[f] = total; total += up256(st->bytes[f]); placed[f] = true; };
+  for (int f : kArenaGroupA) place(f);
+  for (int f : kArenaGroupB) place(f);
+  for (int f : kArenaGroupC) place(f);
+  place(CLOUDSC_F_PAPH);
+  for (int f = 0; f < CLOUDSC_NFIELDS; ++f)
+    if (is_live(f) && !placed[f]) place(f);
+  cudaError_t e = cudaMalloc(&st->arena, total);
+  if (e != cudaSuccess) { cloudsc_b200_destroy(st); return cuda_fail(e, "cudaMalloc(arena)"); }
+  for (int f = 0; f < CLOUDSC_NFIELDS; ++f) st->dev[f] = is_live(f) ? st->arena + off[f] : nullptr;
+  e = cudaMalloc(&st->plude0, st->bytes[CLOUDSC_F_PLUDE]);
   if (e != cudaSuccess) { cloudsc_b200_destroy(st); return cuda_fail(e, "cudaMalloc(plude0)"); }
+
+  /* tensor maps (whole 32-column rows: NPROMA must be a multiple of 32) */
+  st->has_tm = false;
+  if (nproma % 32 == 0) {
+    const cuuint64_t np = (cuuint64_t)nproma, kl = (cuuint64_t)klev, nb = (cuuint64_t)st->nblocks;
+    const cuuint64_t rowb = np * 8, SL = up256(st->bytes[CLOUDSC_F_PT]), SC = up256(st->bytes[CLOUDSC_F_PCLV]);
+    const cuuint64_t dA[4] = {np, kl, nb, 15}, sA[3] = {rowb, kl * rowb, SL};
+    const cuuint32_t bA[4] = {32, 1, 1, 15};
+    const cuuint64_t dB[4] = {np, kl, nb, 3};
+    const cuuint32_t bB[4] = {32, 1, 1, 3};
+    const cuuint64_t dC[5] = {np, kl, 5, nb, 2}, sC[4] = {rowb, kl * rowb, 5 * kl * rowb, SC};
+    const cuuint32_t bC[5] = {32, 1, 4, 1, 2};
+    const cuuint64_t dH[3] = {np, kl + 1, nb}, sH[2] = {rowb, (kl + 1) * rowb};
+    const cuuint32_t bH[3] = {32, 1, 1};
+    st->has_tm = encode_map(&st->tm.a, st->dev[kArenaGroupA[0]], 4, dA, sA, bA) &&
+                 encode_map(&st->tm.b, st->dev[kArenaGroupB[0]], 4, dB, sA, bB) &&
+                 encode_map(&st->tm.c, st->dev[kArenaGroupC[0]], 5, dC, sC, bC) &&
+                 encode_map(&st->tm.h, st->dev[CLOUDSC_F_PAPH], 3, dH, sH, bH);
+  }
   *out = st;
   return 0;
 }
 
 int cloudsc_b200_destroy(cloudsc_b200_state *st) {
   if (!st) return 0;
-  for (int f = 0; f < CLOUDSC_NFIELDS; ++f)
-    if (st->dev[f]) cudaFree(st->dev[f]);
+  if (st->arena) cudaFree(st->arena);
   if (st->plude0) cudaFree(st->plude0);
   free(st);
   return 0;
@@ -282,7 +343,17 @@ int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, in
   long long end = (long long)(first_block + nblocks) * st->nproma;
   if (end > st->ngptot) end = st->ngptot;
   LaunchGeom g{first_block * st->nproma, (int)end, st->nproma, st->klev};
-  CU(launch_sweep(ft, g, ptsphy, st->precision, g_variant, (cudaStream_t)stream));
+  if (st->has_tm && g_variant == VARIANT_AUTO)
+    CU(launch_sweep_tmap(ft, st->tm, g, ptsphy, (cudaStream_t)stream));
+  else
+    CU(launch_sweep(ft, g, ptsphy, st->precision, g_variant, (cudaStream_t)stream));
+  return 0;
+}
+
+int cloudsc_b200_state_kernel_info(cloudsc_b200_state *st, int out[8]) {
+  if (!st || !out) return fail(CLOUDSC_B200_EARG, "state_kernel_info: NULL argument");
+  if (st->has_tm && g_variant == VARIANT_AUTO) CU(tmap_kernel_info(out));
+  else CU(sweep_kernel_info(st->nproma, st->precision, g_variant, out));
   return 0;
 }
 

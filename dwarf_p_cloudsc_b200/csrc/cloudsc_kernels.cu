@@ -281,6 +281,134 @@ cloudsc_sweep_tile(const __grid_constant__ FieldTable ft, const LaunchGeom g, co
   cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
 }
 
+/* ---- IO policy 4: tensor-map TMA on an arena-allocated input set --------------------------------- */
+/*
+ * Issuing a bulk copy costs the issuing warp ~50 cycles whatever its size (measured: 27 copies per level
+ * = 1500-5000 cycles of a 6000-15000-cycle level, tools/gpu_level_timing.py), so the number of requests
+ * matters more than their bytes.  When the input fields come from ONE arena with a constant spacing
+ * between fields of the same kind (cloudsc_b200_create), a 4-/5-dimensional tensor map describes
+ * (column, level, [species,] block, field) and one `cp.async.bulk.tensor` request brings the rows of
+ * all fields of a group: 4 requests per level instead of 27.  Same 2-stage ring, same mbarriers, same
+ * consumer (one LDS per value) as IO policy 2 with one-warp CTAs.
+ */
+const int kArenaGroupA[15] = {CLOUDSC_F_PT, CLOUDSC_F_PQ, CLOUDSC_F_TENDENCY_TMP_T, CLOUDSC_F_TENDENCY_TMP_Q,
+                              CLOUDSC_F_TENDENCY_TMP_A, CLOUDSC_F_PA, CLOUDSC_F_PAP, CLOUDSC_F_PSUPSAT, CLOUDSC_F_PLUDE,
+                              CLOUDSC_F_PSNDE, CLOUDSC_F_PHRSW, CLOUDSC_F_PHRLW, CLOUDSC_F_PVERVEL, CLOUDSC_F_PVFL,
+                              CLOUDSC_F_PVFI};
+const int kArenaGroupB[3] = {CLOUDSC_F_PLU, CLOUDSC_F_PMFU, CLOUDSC_F_PMFD};
+const int kArenaGroupC[2] = {CLOUDSC_F_PCLV, CLOUDSC_F_TENDENCY_TMP_CLD};
+
+/* shared-memory row of an input slot: group a rows 0-14, b 15-17, c 18-25 ([field][species]), h 26 */
+__host__ __device__ constexpr int tmap_row(int s) {
+  return s == IN_PT ? 0 : s == IN_PQ ? 1 : s == IN_TT ? 2 : s == IN_TQ ? 3 : s == IN_TA ? 4 : s == IN_PA ? 5
+       : s == IN_PAP ? 6 : s == IN_PSUPSAT ? 7 : s == IN_PLUDE ? 8 : s == IN_PSNDE ? 9 : s == IN_PHRSW ? 10
+       : s == IN_PHRLW ? 11 : s == IN_PVERVEL ? 12 : s == IN_PVFL ? 13 : s == IN_PVFI ? 14
+       : s == IN_PLU ? 15 : s == IN_PMFU ? 16 : s == IN_PMFD ? 17
+       : (s >= IN_PCLV0 && s <= IN_PCLV3) ? 18 + (s - IN_PCLV0)
+       : (s >= IN_TCLD0 && s <= IN_TCLD3) ? 22 + (s - IN_TCLD0) : 26;
+}
+
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *tm, unsigned bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap *tm, unsigned bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(unsigned dst, const CUtensorMap *tm, unsigned bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+template <typename T>
+struct TmapIO {
+  static constexpr int kCols = 32;
+  static constexpr int kRow = kCols * (int)sizeof(T);
+  static constexpr int kStage = N_IN * kRow;
+  static constexpr int kSmem = 2 * kStage + 32;
+  const FieldTable &ft;
+  const TensorMaps &tm;
+  int ibl, jl0;                       /* NPROMA block and first column (inside it) of this warp */
+  int stride, klev;
+  unsigned smem0, bar0;               /* shared addresses of stage 0 and of full[0] (full[1] at +8) */
+  const T *stage_t;                   /* generic pointer: stage 0 + lane */
+  const T *cur;
+  long long offH, off1;
+  unsigned cL, cH1, cC, spstride;     /* 32-bit element offsets of the current level's output rows */
+
+  __device__ __forceinline__ void issue(int level) {   /* one elected lane */
+    const unsigned st = (unsigned)level & 1u;
+    const unsigned bar = bar0 + 8u * st;
+    const unsigned dst = smem0 + st * (unsigned)kStage;
+    mbar_arrive_expect_tx(bar, (unsigned)kStage);
+    tma_load_4d(dst, &tm.a, bar, jl0, level, ibl, 0);
+    /* row level+1 of plu/pmfu/pmfd does not exist at the last level: the request is out of bounds there,
+       TMA fills zeros (never consumed) and still reports the full box to the mbarrier */
+    tma_load_4d(dst + 15u * kRow, &tm.b, bar, jl0, level + 1, ibl, 0);
+    tma_load_5d(dst + 18u * kRow, &tm.c, bar, jl0, level, 0, ibl, 0);
+    tma_load_3d(dst + 26u * kRow, &tm.h, bar, jl0, level + 1, ibl);
+  }
+  __device__ __forceinline__ void level_begin(int k) {
+    cur = stage_t + (k & 1) * (kStage / (int)sizeof(T));
+    mbar_wait(bar0 + 8u * ((unsigned)k & 1u), ((unsigned)k >> 1) & 1u);
+  }
+  __device__ __forceinline__ void level_end(int k) {
+    __syncwarp();               /* every lane is done reading stage k&1 */
+    if (k + 2 < klev) {
+      if (elect_one()) issue(k + 2);
+      __syncwarp();
+    }
+    cL += (unsigned)stride; cH1 += (unsigned)stride; cC += (unsigned)stride;
+  }
+  template <int S> __device__ __forceinline__ T ld(int) const { return cur[tmap_row(S) * kCols]; }
+  template <int S> __device__ __forceinline__ T ld_next(int) const { return cur[tmap_row(S) * kCols]; }
+  __device__ __forceinline__ T paph_row(int r) const {
+    return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PAPH]) + offH + (long long)r * stride);
+  }
+  template <int S> __device__ __forceinline__ void st(int, T v) {
+    const unsigned off = out_kind(S) == 0 ? cL : out_kind(S) == 1 ? cH1 : cC + (unsigned)out_species(S) * spstride;
+    __stcs(static_cast<T *>(ft.p[out_field(S)]) + off, v);
+  }
+  template <int S> __device__ __forceinline__ void st_row0(T v) {
+    __stcs(static_cast<T *>(ft.p[out_field(S)]) + (cH1 - (unsigned)stride), v);
+  }
+  __device__ __forceinline__ T plsm() const { return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PLSM]) + off1); }
+  __device__ __forceinline__ int ktype() const { return __ldg(static_cast<const int *>(ft.p[CLOUDSC_F_KTYPE]) + off1); }
+  __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(32, 12)
+cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant__ TensorMaps tm, const LaunchGeom g,
+                   const __grid_constant__ StepConst<T> sc) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using IO = TmapIO<T>;
+  const int ccol = g.col_begin + blockIdx.x * IO::kCols;   /* col_begin, col_end, nproma: multiples of 32 (launcher) */
+  if (ccol >= g.col_end) return;
+  const int ibl = ccol / g.nproma;
+  const int jl0 = ccol - ibl * g.nproma;
+  const int jl = jl0 + (int)threadIdx.x;
+  const long long bL = (long long)ibl * g.klev * g.nproma, bH = (long long)ibl * (g.klev + 1) * g.nproma;
+  IO io{ft, tm, ibl, jl0, g.nproma, g.klev,
+        smem_u32(smem_raw), smem_u32(smem_raw + 2 * IO::kStage),
+        reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
+        bH + jl, (long long)ibl * g.nproma + jl,
+        (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma)};
+  if (threadIdx.x == 0) {
+    mbar_init(io.bar0, 1);
+    mbar_init(io.bar0 + 8, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (elect_one()) {
+    io.issue(0);
+    if (g.klev > 1) io.issue(1);
+  }
+  __syncwarp();
+  cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+}
+
 /* ---- IO policy 3: thread-private cp.async ring, pre-offset slot pointers, streaming stores -------- */
 /*
  * Every thread stages ITS OWN column: per level 27 `cp.async` (SASS LDGSTS, 8 bytes each, a warp
@@ -605,6 +733,56 @@ static cudaError_t launch_any(const FieldTable &ft, const LaunchGeom &g, double 
   /* geometry the TMA path cannot take (NPROMA not a multiple of 32, unaligned column range or
      pointers): same arithmetic, plain global loads */
   return launch_direct<T>(ft, g, ptsphy, is_tile(variant) ? VARIANT_DIRECT_R168 : variant, stream);
+}
+
+cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
+                              cudaStream_t stream) {
+  if (g.col_end <= g.col_begin) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const void *fn = (const void *)cloudsc_sweep_tmap<double>;
+  const size_t smem = TmapIO<double>::kSmem;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  /* whole 32-column rows through TMA; a ragged tail (< 32 columns) goes to the plain-load kernel */
+  const int aligned_end = g.col_end - (g.col_end - g.col_begin) % 32;
+  if (aligned_end > g.col_begin) {
+    LaunchGeom ga = g;
+    ga.col_end = aligned_end;
+    StepConst<double> sc;
+    fill_step<double>(host_consts<double>(dev), ptsphy, &sc);
+    const int grid = (aligned_end - g.col_begin) / 32;
+    void *args[] = {(void *)&ft, (void *)&tm, (void *)&ga, (void *)&sc};
+    e = cudaLaunchKernel(fn, dim3(grid), dim3(32), args, smem, stream);
+    if (e != cudaSuccess) return e;
+  }
+  if (aligned_end < g.col_end) {
+    LaunchGeom gt = g;
+    gt.col_begin = aligned_end;
+    e = launch_direct<double>(ft, gt, ptsphy, VARIANT_DIRECT_R168, stream);
+  }
+  return e;
+}
+
+cudaError_t tmap_kernel_info(int out[8]) {
+  const void *fn = (const void *)cloudsc_sweep_tmap<double>;
+  const size_t dyn = TmapIO<double>::kSmem;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes a;
+  e = cudaFuncGetAttributes(&a, fn);
+  if (e != cudaSuccess) return e;
+  int nb = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 32, dyn);
+  if (e != cudaSuccess) return e;
+  out[0] = a.numRegs; out[1] = (int)a.localSizeBytes; out[2] = (int)a.sharedSizeBytes; out[3] = a.maxThreadsPerBlock;
+  out[4] = nb; out[5] = 32; out[6] = 100; out[7] = (int)dyn;
+  return cudaSuccess;
 }
 
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,

@@ -5,6 +5,7 @@
 #ifndef CLOUDSC_KERNELS_CUH
 #define CLOUDSC_KERNELS_CUH
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "cloudsc_b200.h"
 #include "cloudsc_consts.h"
@@ -44,6 +45,26 @@ enum Variant {
   VARIANT_PIPE_W16 = 11,
   VARIANT_COUNT
 };
+
+/*
+ * Tensor maps of an ARENA-allocated input set (cloudsc_b200_create): fields of one kind lie at a
+ * constant spacing, so ONE tensor-map TMA request fetches the rows of many fields.
+ *   a : the 15 [klev] inputs consumed at their own level   box {32 cols, 1 level, 1 block, 15 fields}
+ *   b : plu, pmfu, pmfd (consumed one level ahead)          box {32, 1, 1, 3}
+ *   c : pclv, tendency_tmp_cld, species 0..3                box {32, 1, 4 species, 1 block, 2 fields}
+ *   h : paph                                                box {32, 1, 1}
+ */
+struct alignas(64) TensorMaps {
+  CUtensorMap a, b, c, h;
+};
+/* order of the fields inside the arena groups (the kernel's shared-memory rows follow it) */
+extern const int kArenaGroupA[15];
+extern const int kArenaGroupB[3];
+extern const int kArenaGroupC[2];
+
+cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
+                              cudaStream_t stream);
+cudaError_t tmap_kernel_info(int out[8]);
 
 cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<float> &c32);
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,

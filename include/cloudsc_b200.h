@@ -138,6 +138,11 @@ int cloudsc_b200_run_host(void *const host_fields[CLOUDSC_NFIELDS], int ngptot, 
 int cloudsc_b200_release_cache(void);
 
 /* ---- handle API: resident device state for a fixed geometry (one handle per GPU) --------- */
+/*
+ * The state owns ONE device arena in which the fields of a kind lie at a constant spacing.  That lets
+ * step() describe the inputs with four tensor maps and fetch a level's 27 input rows with 4 TMA requests
+ * instead of 27; cloudsc_b200_launch() on caller-owned pointers cannot assume that.
+ */
 typedef struct cloudsc_b200_state cloudsc_b200_state;
 int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc_b200_state **out);
 int cloudsc_b200_destroy(cloudsc_b200_state *st);
@@ -149,6 +154,9 @@ int cloudsc_b200_download(cloudsc_b200_state *st, void *const host_fields[CLOUDS
 int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, int nblocks, void *stream);
 /* restore PLUDE from the pristine copy kept at upload() (the kernel scales it in place) */
 int cloudsc_b200_reset_inout(cloudsc_b200_state *st, void *stream);
+/* kernel_info of the kernel step() launches for this state (the arena-backed tensor-map TMA kernel when
+ * NPROMA is a multiple of 32) */
+int cloudsc_b200_state_kernel_info(cloudsc_b200_state *st, int out[8]);
 /* device pointer of field f inside the state (for zero-copy consumers) */
 void *cloudsc_b200_field_ptr(cloudsc_b200_state *st, int f);
 int cloudsc_b200_sync(void *stream);

@@ -296,3 +296,37 @@ def test_columns_are_independent(built, input_data):
         u1 = state.unblock(G1[f.name], ngptot)[..., :100]
         u2 = state.unblock(G2[f.name], ngptot)
         assert np.array_equal(u2, u1[..., idx]), f.name
+
+
+@pytest.mark.parametrize("ngptot,nproma,perturbation", [(1000, 128, ""), (257, 32, ""), (1221, 64, "warm+land+conv+rain+moist+tend"),
+                                                        (4096, 256, "hot+rain+moist+conv"), (100, 100, "")])
+def test_arena_state_tensor_map_kernel_matches_oracle(built, oracle, input_data, ngptot, nproma, perturbation):
+    """cloudsc_b200_create/upload/step/download: the arena-backed state whose step() fetches a level's
+    inputs with 4 tensor-map TMA requests (NPROMA multiple of 32; plain kernel otherwise), in block ranges."""
+    from dwarf_p_cloudsc_b200 import params, state, api, validate
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    src = state.perturb(cols, perturbation) if perturbation else cols
+    F = state.blocked_fields(src, ngptot, nproma, klev)
+    # the CPU reference keeps ~51 KB of stack temporaries per column of a block: run it with NPROMA <= 128
+    # and compare column by column (the result of a column does not depend on the blocking)
+    onp = min(nproma, 128)
+    R = state.blocked_fields(src, ngptot, onp, klev)
+    oracle.run(R, p, k, ngptot, onp, klev, scalars["PTSPHY"], 0)
+    api.set_params(p, k)
+    st = api.State(ngptot, nproma, klev)
+    try:
+        info = st.kernel_info()
+        assert (info["variant"] == 100) == (nproma % 32 == 0), info      # 100 = the tensor-map kernel
+        st.upload(F)
+        nb = state.nblocks_of(ngptot, nproma)
+        half = nb // 2
+        if half:
+            st.step(scalars["PTSPHY"], 0, half)
+        st.step(scalars["PTSPHY"], half, nb - half)
+        st.download(F)
+        st.sync()
+    finally:
+        st.close()
+    errs = [validate.field_error(n, state.unblock(F[n], ngptot), state.unblock(R[n], ngptot), ngptot) for n in state.VALIDATE_ORDER]
+    assert validate.all_pass(errs), "\n" + validate.format_table(errs)
