@@ -12,6 +12,7 @@
 #include "cloudsc_fill.h"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace cloudsc {
 
@@ -349,17 +350,30 @@ struct TmapIO {
     tma_load_5d(dst + 18u * kRow, &tm.c, bar, jl0, level, 0, ibl, 0);
     tma_load_3d(dst + 26u * kRow, &tm.h, bar, jl0, level + 1, ibl);
   }
+  /* -DCLOUDSC_TIMING (tools/build_alt.sh timing -DCLOUDSC_TIMING; tools/gpu_level_timing.py): four clock stamps
+     per level of every 512th CTA into the TENDENCY_CML_T buffer, which the kernel never touches otherwise */
+#ifdef CLOUDSC_TIMING
+#define CLOUDSC_TSTAMP(i)                                                                        \
+  if (threadIdx.x == 0 && blockIdx.x % 512 == 0 && ft.p[CLOUDSC_F_TENDENCY_CML_T])               \
+    static_cast<long long *>(ft.p[CLOUDSC_F_TENDENCY_CML_T])[(blockIdx.x / 512) * 4 * klev + 4 * k + (i)] = clock64()
+#else
+#define CLOUDSC_TSTAMP(i)
+#endif
   __device__ __forceinline__ void level_begin(int k) {
     cur = stage_t + (k & 1) * (kStage / (int)sizeof(T));
+    CLOUDSC_TSTAMP(0);
     mbar_wait(bar0 + 8u * ((unsigned)k & 1u), ((unsigned)k >> 1) & 1u);
+    CLOUDSC_TSTAMP(1);
   }
   __device__ __forceinline__ void level_end(int k) {
+    CLOUDSC_TSTAMP(2);
     __syncwarp();               /* every lane is done reading stage k&1 */
     if (k + 2 < klev) {
       if (elect_one()) issue(k + 2);
       __syncwarp();
     }
     cL += (unsigned)stride; cH1 += (unsigned)stride; cC += (unsigned)stride;
+    CLOUDSC_TSTAMP(3);
   }
   template <int S> __device__ __forceinline__ T ld(int) const { return cur[tmap_row(S) * kCols]; }
   template <int S> __device__ __forceinline__ T ld_next(int) const { return cur[tmap_row(S) * kCols]; }
