@@ -562,15 +562,10 @@ cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<fl
 namespace {
 constexpr int kDirectBlock = 128;
 
-/* register budget of the direct kernel = 65536 / (128 * MINB): 2 -> 255, 3 -> 168, 4 -> 128 */
-inline int direct_minb(int variant) {
-  switch (variant) {
-    case VARIANT_DIRECT_R255: return 2;
-    case VARIANT_DIRECT_R128: return 4;
-    case VARIANT_DIRECT_R168:
-    default: return 3;
-  }
-}
+/* Every kernel is built for ONE register budget: 168 registers = 3 warps per scheduler = 12 per SM.  255 registers
+   (8 warps/SM) lose more latency hiding than they gain in scheduling freedom, 128 registers (16 warps/SM) spill
+   and still need 3 waves for 163 840 columns (profiles/README.md); those builds were measured and dropped. */
+
 
 template <typename T, int MINB>
 cudaError_t launch_direct_mb(const FieldTable &ft, const LaunchGeom &g, double ptsphy, cudaStream_t stream) {
@@ -587,20 +582,14 @@ cudaError_t launch_direct_mb(const FieldTable &ft, const LaunchGeom &g, double p
 
 template <typename T>
 cudaError_t launch_direct(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int variant, cudaStream_t stream) {
-  switch (direct_minb(variant)) {
-    case 2: return launch_direct_mb<T, 2>(ft, g, ptsphy, stream);
-    case 4: return launch_direct_mb<T, 4>(ft, g, ptsphy, stream);
-    default: return launch_direct_mb<T, 3>(ft, g, ptsphy, stream);
-  }
+  (void)variant;
+  return launch_direct_mb<T, 3>(ft, g, ptsphy, stream);
 }
 
 template <typename T>
 const void *direct_fn(int variant) {
-  switch (direct_minb(variant)) {
-    case 2: return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 2>;
-    case 4: return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 4>;
-    default: return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 3>;
-  }
+  (void)variant;
+  return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 3>;
 }
 
 /* ---- tile (TMA-staged) variant ------------------------------------------------------------------ */
@@ -615,9 +604,9 @@ inline TileCfg tile_cfg(int variant, int nproma) {
      -- the fastest configuration measured on B200 (profiles/README.md) */
   TileCfg c = {widest ? 1 : 0, 12};
   switch (variant) {
-    case VARIANT_TILE_C4_W8: c.warps = widest; c.wps = 8; break;
-    case VARIANT_TILE_C4_W12: c.warps = widest; break;
-    case VARIANT_TILE_C4_W16: c.warps = widest; c.wps = 16; break;
+    case VARIANT_TILE_C4_W8:
+    case VARIANT_TILE_C4_W12:
+    case VARIANT_TILE_C4_W16: c.warps = widest; break;
     case VARIANT_TILE_C2_W12: c.warps = widest >= 2 ? 2 : widest; break;
     default: break;
   }
@@ -626,9 +615,7 @@ inline TileCfg tile_cfg(int variant, int nproma) {
 }
 
 #define CLOUDSC_TILE_DISPATCH(cfg, ...)                                                   \
-  if (cfg.warps == 4 && cfg.wps == 8) { constexpr int W = 4, MB = 2; __VA_ARGS__; }       \
-  else if (cfg.warps == 4 && cfg.wps == 16) { constexpr int W = 4, MB = 4; __VA_ARGS__; } \
-  else if (cfg.warps == 4) { constexpr int W = 4, MB = 3; __VA_ARGS__; }                  \
+  if (cfg.warps == 4) { constexpr int W = 4, MB = 3; __VA_ARGS__; }                       \
   else if (cfg.warps == 2) { constexpr int W = 2, MB = 6; __VA_ARGS__; }                  \
   else { constexpr int W = 1, MB = 12; __VA_ARGS__; }
 
@@ -693,11 +680,8 @@ SlotTable make_slot_table(const FieldTable &ft, const LaunchGeom &g) {
 
 template <typename T>
 const void *pipe_fn(int wps) {
-  switch (wps) {
-    case 8: return (const void *)cloudsc_sweep_pipe<T, kPipeBlock, 8>;
-    case 16: return (const void *)cloudsc_sweep_pipe<T, kPipeBlock, 16>;
-    default: return (const void *)cloudsc_sweep_pipe<T, kPipeBlock, 12>;
-  }
+  (void)wps;
+  return (const void *)cloudsc_sweep_pipe<T, kPipeBlock, 12>;
 }
 
 template <typename T>

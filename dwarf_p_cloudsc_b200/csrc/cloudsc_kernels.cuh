@@ -26,20 +26,21 @@ struct LaunchGeom {
 };
 
 enum Variant {
-  VARIANT_AUTO = 0,
-  /* one thread per column, loads/stores straight from/to global memory; three register budgets */
-  VARIANT_DIRECT_R255 = 1,  /* 2 CTAs of 128 threads per SM */
-  VARIANT_DIRECT_R168 = 2,  /* 3 CTAs per SM */
-  VARIANT_DIRECT_R128 = 3,  /* 4 CTAs per SM */
+  VARIANT_AUTO = 0,         /* = VARIANT_TILE_C1_W12 where NPROMA allows, else the direct kernel */
+  /* one thread per column, loads/stores straight from/to global memory (any geometry) */
+  VARIANT_DIRECT_R255 = 1,  /* (1 and 3: former 255-/128-register builds, now aliases of 2) */
+  VARIANT_DIRECT_R168 = 2,
+  VARIANT_DIRECT_R128 = 3,
   /* TMA-staged input tiles (cp.async.bulk + mbarrier) of 32*WARPS columns per CTA, streaming stores.
-     Cn = warps per CTA (clamped to what NPROMA allows), Wm = resident-warp target per SM that sets the
-     register budget (8 -> 255, 12 -> 168, 16 -> 128 registers). */
+     Cn = warps per CTA (clamped to what NPROMA allows); all at 168 registers = 12 resident warps per SM
+     (4 and 6: former 255-/128-register builds, now aliases of 5) */
   VARIANT_TILE_C4_W8 = 4,
   VARIANT_TILE_C4_W12 = 5,
   VARIANT_TILE_C4_W16 = 6,
-  VARIANT_TILE_C1_W12 = 7,  /* one-warp CTAs, warp-private tiles; the default (VARIANT_AUTO) */
+  VARIANT_TILE_C1_W12 = 7,  /* one-warp CTAs, warp-private tiles */
   VARIANT_TILE_C2_W12 = 8,
-  /* thread-private cp.async ring (LDGSTS), pre-offset slot pointers, streaming stores; any geometry */
+  /* thread-private cp.async ring (LDGSTS), pre-offset slot pointers, streaming stores; any geometry
+     (10 and 11: aliases of 9) */
   VARIANT_PIPE_W12 = 9,
   VARIANT_PIPE_W8 = 10,
   VARIANT_PIPE_W16 = 11,
