@@ -8,7 +8,7 @@ from dwarf_p_cloudsc_b200 import api, params, state
 cols, scalars, _, klev = state.load_input()
 p, k = params.params_from_scalars(scalars)
 api.set_params(p, k)
-ngptot, nproma = 163840, 128
+ngptot, nproma = (int(sys.argv[1]) if len(sys.argv) > 1 else 163840), 128
 F = state.blocked_fields(cols, ngptot, nproma, klev)
 st = api.State(ngptot, nproma, klev)
 st.upload(F)
@@ -25,11 +25,11 @@ for it in range(3):
     torch.cuda.synchronize()
 t = dbg.cpu().numpy().reshape(10, klev, 4)
 def seg(x, lo, hi): return x[lo:hi].mean()
-for c in range(10):
+for c in range(min(10, (ngptot // 32 + 511) // 512)):
     beg, aft, endin, endout = (t[c, :, i] for i in range(4))
     lev = np.diff(beg); wait = aft - beg; body = endin - aft; issue = endout - endin
     print("CTA %4d total %8d | level: top14 %6.0f k14-80 %6.0f k81+ %6.0f | wait %5.0f %5.0f %5.0f | body %6.0f %6.0f %6.0f | refill issue %5.0f %5.0f %5.0f" % (
         c * 512, beg[-1] - beg[0], seg(lev, 0, 14), seg(lev, 14, 80), seg(lev, 81, 136),
         seg(wait, 0, 14), seg(wait, 14, 80), seg(wait, 81, 137), seg(body, 0, 14), seg(body, 14, 80), seg(body, 81, 137),
         seg(issue, 0, 14), seg(issue, 14, 80), seg(issue, 81, 137)))
-print("body cycles of CTA 1536 per level:", (t[3, :, 2] - t[3, :, 1]).astype(int).tolist())
+
