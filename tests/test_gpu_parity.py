@@ -330,3 +330,47 @@ def test_arena_state_tensor_map_kernel_matches_oracle(built, oracle, input_data,
         st.close()
     errs = [validate.field_error(n, state.unblock(F[n], ngptot), state.unblock(R[n], ngptot), ngptot) for n in state.VALIDATE_ORDER]
     assert validate.all_pass(errs), "\n" + validate.format_table(errs)
+
+
+@pytest.mark.parametrize("lev0,lev1", [(97, 137), (0, 30), (60, 63)])
+def test_other_column_heights(built, oracle, input_data, lev0, lev1):
+    """Nothing is specialised on KLEV = 137: a slab of the levels (with its own half-level pressures) is a
+    valid, shorter column set for the reference kernel and for both device paths."""
+    import torch
+    from dwarf_p_cloudsc_b200 import params, state, api, validate
+    cols, scalars, klon, _ = input_data
+    p, k = params.params_from_scalars(scalars)
+    if lev1 - lev0 < 16:
+        p.ncldtop = 2
+    klev = lev1 - lev0
+    sub = {}
+    for f in params.FIELDS:
+        if f.name not in cols:
+            continue
+        a = cols[f.name]
+        if f.kind == "L":
+            sub[f.name] = np.ascontiguousarray(a[lev0:lev1])
+        elif f.kind == "H":
+            sub[f.name] = np.ascontiguousarray(a[lev0:lev1 + 1])
+        elif f.kind == "C":
+            sub[f.name] = np.ascontiguousarray(a[:, lev0:lev1])
+        else:
+            sub[f.name] = a
+    ngptot, nproma = 700, 64
+    F = state.blocked_fields(sub, ngptot, nproma, klev)
+    R = {n: a.copy() for n, a in F.items()}
+    oracle.run(R, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 0)
+    api.set_params(p, k)
+    G = {n: a.copy() for n, a in F.items()}
+    st = api.State(ngptot, nproma, klev)
+    try:
+        st.upload(G); st.step(scalars["PTSPHY"]); st.download(G); st.sync()
+    finally:
+        st.close()
+    errs = validate.validate(G, R, ngptot)
+    assert validate.all_pass(errs), "\n" + validate.format_table(errs)
+    D = {n: torch.from_numpy(a).cuda() for n, a in F.items()}
+    api.launch(D, ngptot, nproma, klev, scalars["PTSPHY"])
+    torch.cuda.synchronize()
+    errs = validate.validate({n: t.cpu().numpy() for n, t in D.items()}, R, ngptot)
+    assert validate.all_pass(errs), "\n" + validate.format_table(errs)
