@@ -374,3 +374,28 @@ def test_other_column_heights(built, oracle, input_data, lev0, lev1):
     torch.cuda.synchronize()
     errs = validate.validate({n: t.cpu().numpy() for n, t in D.items()}, R, ngptot)
     assert validate.all_pass(errs), "\n" + validate.format_table(errs)
+
+
+def test_full_size_properties_arena_state(built, input_data):
+    """The path bench.py times, at its size (163840 x 128, resident arena state, tensor-map kernel):
+    replication invariance (column g == column g mod 100, bitwise), agreement of the first 100 columns with
+    reference.h5, and bitwise agreement with the kernel behind cloudsc_b200_launch on caller-owned fields."""
+    from dwarf_p_cloudsc_b200 import params, state, api, validate
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    ngptot, nproma = 163840, 128
+    F = state.blocked_fields(cols, ngptot, nproma, klev)
+    G2 = _run_gpu({n: a.copy() for n, a in F.items()}, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
+    st = api.State(ngptot, nproma, klev)
+    try:
+        st.upload(F); st.step(scalars["PTSPHY"]); st.download(F); st.sync()
+    finally:
+        st.close()
+    ref = state.load_reference()
+    idx = np.arange(ngptot) % 100
+    for name in state.VALIDATE_ORDER:
+        u = state.unblock(F[name], ngptot)
+        base = u[..., :100]
+        assert np.array_equal(u, base[..., idx]), f"{name}: replicated columns differ"
+        assert validate.field_error(name, base, ref[name], 100).passes(), name
+        assert np.array_equal(u, state.unblock(G2[name], ngptot)), f"{name}: the two device paths differ"
