@@ -1,0 +1,21 @@
+"""run_host pipeline tuning: wall time of the end-to-end call for several (chunk_blocks, nstreams)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dwarf_p_cloudsc_b200 import api, params, state
+cols, scalars, _, klev = state.load_input()
+p, k = params.params_from_scalars(scalars)
+api.set_params(p, k)
+ngptot, nproma = 163840, 128
+pts = float(scalars["PTSPHY"])
+F = state.blocked_fields(cols, ngptot, nproma, klev)
+H = {n: torch.from_numpy(a).pin_memory() for n, a in F.items()}
+plude0 = H["PLUDE"].clone()
+for chunk, ns in [(0, 0), (54, 4), (107, 4), (160, 4), (320, 4), (54, 3), (107, 3), (107, 6), (54, 8), (27, 8), (214, 2), (320, 2)]:
+    ts = []
+    for it in range(4):
+        H["PLUDE"].copy_(plude0)
+        t0 = time.perf_counter()
+        st = api.run_host(H, ngptot, nproma, klev, pts, chunk, ns)
+        ts.append(1e3 * (time.perf_counter() - t0))
+    print("chunk_blocks %4d nstreams %d : %s ms (kernel sum %.1f ms)" % (chunk, ns, " ".join("%.1f" % x for x in ts), st["kernel_ms"]), flush=True)
