@@ -182,7 +182,8 @@ def cpu_arm(ngptot_target, seconds_target=12.0, nthreads=0):
 def run_reference(args, rank):
     if rank != 0:
         return
-    orc, cols, scalars, klev, p, k, cores, n, once = cpu_arm(NGPTOT, seconds_target=4.0)
+    # bounded sample: a step is at most the full 163 840 columns (~0.7 s on 16 cores) and the whole run ~45 s
+    orc, cols, scalars, klev, p, k, cores, n, once = cpu_arm(NGPTOT, seconds_target=min(4.0, max(0.05, 45.0 / max(args.steps, 1))))
     for _ in range(max(args.warmup, 1) - 1):
         once(n)
     ts = [once(n) for _ in range(args.steps)]
