@@ -136,7 +136,28 @@ def perturb(cols: Dict[str, np.ndarray], variant: str, seed: int = 1234) -> Dict
     if "tend" in parts:        # non-trivial incoming tendencies, tiny/negative condensate
         c["TENDENCY_TMP_T"] = c["TENDENCY_TMP_T"] + 2.0e-4 * (rng.random(c["PT"].shape) - 0.5)
         c["TENDENCY_TMP_CLD"][:4] = c["TENDENCY_TMP_CLD"][:4] + 2.0e-9 * (rng.random((4,) + c["PT"].shape) - 0.5)
-    unknown = parts - {"warm", "hot", "land", "conv", "rain", "moist", "tend", ""}
+    if "sparse" in parts:      # isolated events in otherwise clear, dry air; precipitation falling into clear layers
+        shape = c["PT"].shape
+        clear = rng.random((1, nlon)) < 0.5                                   # half of the columns: no cloud at all ...
+        band = (lev > 0.35) & (lev < 0.55)                                    # ... except one thin layer of ice and snow aloft
+        c["PA"] = np.where(clear, np.where(band, 0.3, 0.0), c["PA"])
+        for m in range(4):
+            c["PCLV"][m] = np.where(clear, 0.0, c["PCLV"][m])
+        c["PCLV"][1] = np.where(clear & band, 2.0e-5, c["PCLV"][1])
+        c["PCLV"][3] = np.where(clear & band, 1.0e-5, c["PCLV"][3])
+        c["PQ"] = np.where(clear & ~band, c["PQ"] * 0.3, c["PQ"])             # dry: outside every humidity window
+        c["TENDENCY_TMP_A"] = np.where(clear, 0.0, c["TENDENCY_TMP_A"])
+        c["TENDENCY_TMP_CLD"][:4] = np.where(clear[None], 0.0, c["TENDENCY_TMP_CLD"][:4])
+        lone = rng.random(shape) < 0.01                                       # lone sources in the clear air
+        c["PSUPSAT"] = np.where(clear & lone, 3.0e-6, c["PSUPSAT"])
+        lone = rng.random(shape) < 0.01
+        c["PSNDE"] = np.where(clear & lone, 1.0e-6, c["PSNDE"])
+        lone = rng.random(shape) < 0.01
+        c["PLUDE"] = np.where(clear & lone, 5.0e-6, c["PLUDE"])
+        c["PLU"] = np.where(clear & lone, 1.0e-4, c["PLU"])
+        lone = rng.random(shape) < 0.01                                       # and lone moist points that open the new-cloud window
+        c["PQ"] = np.where(clear & lone & (lev > 0.5), c["PQ"] * 4.0, c["PQ"])
+    unknown = parts - {"warm", "hot", "land", "conv", "rain", "moist", "tend", "sparse", ""}
     if unknown:
         raise ValueError(f"unknown perturbation {unknown}")
     return c

@@ -13,7 +13,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = ["", "warm", "hot+land", "conv+land", "rain+warm", "moist+tend",
-            "warm+land+conv+rain+moist+tend", "hot+rain+moist+conv"]
+            "warm+land+conv+rain+moist+tend", "hot+rain+moist+conv", "sparse", "sparse+warm+conv"]
 
 
 def _oracles(built):
@@ -75,7 +75,7 @@ def test_port_is_bit_identical_to_reference_build(built, input_data):
 @pytest.mark.parametrize("nssopt", [1, 0, 2, 3])
 def test_device_column_code_host_build_is_bit_identical(built, oracle, input_data, variant, nssopt):
     """The k-cached / sparse-solve re-organisation is value-identical to the reference algorithm."""
-    if nssopt != 1 and variant not in ("moist+tend", "warm+land+conv+rain+moist+tend"):
+    if nssopt != 1 and variant not in ("moist+tend", "warm+land+conv+rain+moist+tend", "sparse"):
         pytest.skip("nssopt sweep only on the variants that reach 3.4b(2)")
     import pyemul
     from dwarf_p_cloudsc_b200 import params, state

@@ -60,7 +60,8 @@ def test_gpu_matches_reference_h5(built, input_data):
 
 @pytest.mark.parametrize("variant,nssopt", [("warm", 1), ("hot+land", 1), ("conv+land", 1), ("rain+warm", 1),
                                             ("moist+tend", 0), ("moist+tend", 2), ("moist+tend", 3),
-                                            ("warm+land+conv+rain+moist+tend", 1), ("hot+rain+moist+conv", 1)])
+                                            ("warm+land+conv+rain+moist+tend", 1), ("hot+rain+moist+conv", 1),
+                                            ("sparse", 1), ("sparse", 0), ("sparse+warm+conv", 1)])
 def test_gpu_matches_oracle_perturbed(built, oracle, input_data, variant, nssopt):
     """Branches the shipped data never takes (warm phase, land, snow detrainment, rain freezing...)."""
     from dwarf_p_cloudsc_b200 import params, state
