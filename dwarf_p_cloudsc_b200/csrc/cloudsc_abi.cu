@@ -233,12 +233,13 @@ EncodeTiledFn encode_tiled_fn() {
   }
   return fn;
 }
-/* rank-R FP64 tensor map over `base`: dims/box innermost first, strides (bytes) of dims 1..R-1 */
-bool encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box) {
+/* rank-R tensor map over `base`: dims/box innermost first, strides (bytes) of dims 1..R-1 */
+bool encode_map(CUtensorMap *m, int precision, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                const cuuint32_t *box) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return fn(m, precision == CLOUDSC_B200_FP32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 inline size_t up256(size_t n) { return (n + 255) / 256 * 256; }
@@ -248,7 +249,7 @@ int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc
   if (!out) return fail(CLOUDSC_B200_EARG, "create: out is NULL");
   *out = nullptr;
   if (int rc = check_geom(ngptot, nproma, klev)) return rc;
-  if (precision != CLOUDSC_B200_FP64) return fail(CLOUDSC_B200_EARG, "resident states are FP64 (use cloudsc_b200_launch for FP32 device fields)");
+  if (precision != CLOUDSC_B200_FP64 && precision != CLOUDSC_B200_FP32) return fail(CLOUDSC_B200_EARG, "bad precision %d", precision);
   cloudsc_b200_state *st = (cloudsc_b200_state *)calloc(1, sizeof(*st));
   if (!st) return fail(CLOUDSC_B200_ENOMEM, "out of host memory");
   st->ngptot = ngptot; st->nproma = nproma; st->klev = klev; st->precision = precision;
@@ -280,7 +281,7 @@ int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc
   st->has_tm = false;
   if (nproma % 32 == 0) {
     const cuuint64_t np = (cuuint64_t)nproma, kl = (cuuint64_t)klev, nb = (cuuint64_t)st->nblocks;
-    const cuuint64_t rowb = np * 8, SL = up256(st->bytes[CLOUDSC_F_PT]), SC = up256(st->bytes[CLOUDSC_F_PCLV]);
+    const cuuint64_t rowb = np * elem_size(CLOUDSC_F_PT, precision), SL = up256(st->bytes[CLOUDSC_F_PT]), SC = up256(st->bytes[CLOUDSC_F_PCLV]);
     const cuuint64_t dA[4] = {np, kl, nb, 15}, sA[3] = {rowb, kl * rowb, SL};
     const cuuint32_t bA[4] = {32, 1, 1, 15};
     const cuuint64_t dB[4] = {np, kl, nb, 3};
@@ -289,10 +290,10 @@ int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc
     const cuuint32_t bC[5] = {32, 1, 4, 1, 2};
     const cuuint64_t dH[3] = {np, kl + 1, nb}, sH[2] = {rowb, (kl + 1) * rowb};
     const cuuint32_t bH[3] = {32, 1, 1};
-    st->has_tm = encode_map(&st->tm.a, st->dev[kArenaGroupA[0]], 4, dA, sA, bA) &&
-                 encode_map(&st->tm.b, st->dev[kArenaGroupB[0]], 4, dB, sA, bB) &&
-                 encode_map(&st->tm.c, st->dev[kArenaGroupC[0]], 5, dC, sC, bC) &&
-                 encode_map(&st->tm.h, st->dev[CLOUDSC_F_PAPH], 3, dH, sH, bH);
+    st->has_tm = encode_map(&st->tm.a, precision, st->dev[kArenaGroupA[0]], 4, dA, sA, bA) &&
+                 encode_map(&st->tm.b, precision, st->dev[kArenaGroupB[0]], 4, dB, sA, bB) &&
+                 encode_map(&st->tm.c, precision, st->dev[kArenaGroupC[0]], 5, dC, sC, bC) &&
+                 encode_map(&st->tm.h, precision, st->dev[CLOUDSC_F_PAPH], 3, dH, sH, bH);
   }
   *out = st;
   return 0;
@@ -344,7 +345,7 @@ int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, in
   if (end > st->ngptot) end = st->ngptot;
   LaunchGeom g{first_block * st->nproma, (int)end, st->nproma, st->klev};
   if (st->has_tm && g_variant == VARIANT_AUTO)
-    CU(launch_sweep_tmap(ft, st->tm, g, ptsphy, (cudaStream_t)stream));
+    CU(launch_sweep_tmap(ft, st->tm, g, ptsphy, st->precision, (cudaStream_t)stream));
   else
     CU(launch_sweep(ft, g, ptsphy, st->precision, g_variant, (cudaStream_t)stream));
   return 0;
@@ -352,7 +353,7 @@ int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, in
 
 int cloudsc_b200_state_kernel_info(cloudsc_b200_state *st, int out[8]) {
   if (!st || !out) return fail(CLOUDSC_B200_EARG, "state_kernel_info: NULL argument");
-  if (st->has_tm && g_variant == VARIANT_AUTO) CU(tmap_kernel_info(out));
+  if (st->has_tm && g_variant == VARIANT_AUTO) CU(tmap_kernel_info(st->precision, out));
   else CU(sweep_kernel_info(st->nproma, st->precision, g_variant, out));
   return 0;
 }

@@ -89,6 +89,11 @@ enum OutSlot {
 template <typename T> CLOUDSC_FN T mx(T a, T b) { return a > b ? a : b; }
 template <typename T> CLOUDSC_FN T mn(T a, T b) { return a < b ? a : b; }
 #if defined(__CUDACC__)
+/* single precision has a one-instruction max/min (FMNMX) */
+CLOUDSC_FN float mx(float a, float b) { return fmaxf(a, b); }
+CLOUDSC_FN float mn(float a, float b) { return fminf(a, b); }
+#endif
+#if defined(__CUDACC__)
 CLOUDSC_FN double ex_lib(double x) { return exp(x); }
 CLOUDSC_FN float ex_lib(float x) { return expf(x); }
 CLOUDSC_FN double pw(double x, double y) { return pow(x, y); }
@@ -155,6 +160,10 @@ CLOUDSC_FN double exp_fast(double x) {
   return p;
 #endif
 }
+/* Single precision: the special-function unit is accurate to ~2 ulp, which is all a 24-bit result can use.
+ * expf() is already branch-free (range reduction + MUFU.EX2); division, sqrt and powf are the library's
+ * branchy IEEE sequences (64 slow-path calls in the FP32 kernel), replaced below by MUFU.RCP + one Newton
+ * step, MUFU.SQRT and ex2(y lg2 x). */
 CLOUDSC_FN float exp_fast(float x) { return ex_lib(x); }
 CLOUDSC_FN double exp_fast_lo(double x) { return exp_fast(mx(x, -700.0)); }
 CLOUDSC_FN float exp_fast_lo(float x) { return ex_lib(x); }
@@ -173,7 +182,15 @@ CLOUDSC_FN double rcp_fast(double x) {
   return 1.0 / x;
 #endif
 }
-CLOUDSC_FN float rcp_fast(float x) { return 1.0f / x; }
+CLOUDSC_FN float rcp_fast(float x) {
+#if defined(__CUDACC__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+  return 1.0f / x;
+#endif
+}
 
 /*
  * log(x) for normal positive x: x = m 2^e with m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1),
@@ -216,7 +233,17 @@ CLOUDSC_FN double log_fast(double x) {
 /* x^y for x > 0 as exp(y log x): relative error ~ |y log x| * 2e-16 (library pow: 0.5 ulp at ~15x the
  * instructions and a call into a spilling slow path).  exp_fast is declared above. */
 CLOUDSC_FN double pow_fast(double x, double y) { return exp_fast_lo(y * log_fast(x)); }
-CLOUDSC_FN float pow_fast(float x, float y) { return pw(x, y); }
+/* x^y = 2^(y lg2 x) on the special-function unit: relative error ~ |y lg2 x| * 2^-22; x = 0 gives 2^-inf = 0 */
+CLOUDSC_FN float pow_fast(float x, float y) {
+#if defined(__CUDACC__)
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y * l));
+  return r;
+#else
+  return pw(x, y);
+#endif
+}
 /* sqrt(x) for normal x > 0: MUFU.RSQ64H seed, two Newton steps on 1/sqrt, one on the root */
 CLOUDSC_FN double sqrt_fast(double x) {
 #if defined(__CUDACC__)
@@ -233,7 +260,15 @@ CLOUDSC_FN double sqrt_fast(double x) {
   return std::sqrt(x);
 #endif
 }
-CLOUDSC_FN float sqrt_fast(float x) { return sq(x); }
+CLOUDSC_FN float sqrt_fast(float x) {
+#if defined(__CUDACC__)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sq(x);
+#endif
+}
 
 #if CLOUDSC_STRICT
 #define CLOUDSC_RCP(x) (one / (x))

@@ -392,8 +392,11 @@ struct TmapIO {
   __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
 };
 
+/* resident warps per SM the one-warp-CTA kernels are sized for: 168 registers in FP64 (12 warps), 128 in FP32 (16) */
+template <typename T> constexpr int warps_per_sm() { return sizeof(T) == 4 ? 16 : 12; }
+
 template <typename T>
-__global__ void __launch_bounds__(32, 12)
+__global__ void __launch_bounds__(32, warps_per_sm<T>())
 cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant__ TensorMaps tm, const LaunchGeom g,
                    const __grid_constant__ StepConst<T> sc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -617,7 +620,7 @@ inline TileCfg tile_cfg(int variant, int nproma) {
 #define CLOUDSC_TILE_DISPATCH(cfg, ...)                                                   \
   if (cfg.warps == 4) { constexpr int W = 4, MB = 3; __VA_ARGS__; }                       \
   else if (cfg.warps == 2) { constexpr int W = 2, MB = 6; __VA_ARGS__; }                  \
-  else { constexpr int W = 1, MB = 12; __VA_ARGS__; }
+  else { constexpr int W = 1, MB = warps_per_sm<T>(); __VA_ARGS__; }
 
 template <typename T>
 const void *tile_fn(TileCfg cfg, size_t *smem) {
@@ -733,14 +736,15 @@ static cudaError_t launch_any(const FieldTable &ft, const LaunchGeom &g, double 
   return launch_direct<T>(ft, g, ptsphy, is_tile(variant) ? VARIANT_DIRECT_R168 : variant, stream);
 }
 
-cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
-                              cudaStream_t stream) {
+template <typename T>
+static cudaError_t launch_sweep_tmap_t(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
+                                       cudaStream_t stream) {
   if (g.col_end <= g.col_begin) return cudaSuccess;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  const void *fn = (const void *)cloudsc_sweep_tmap<double>;
-  const size_t smem = TmapIO<double>::kSmem;
+  const void *fn = (const void *)cloudsc_sweep_tmap<T>;
+  const size_t smem = TmapIO<T>::kSmem;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -750,8 +754,8 @@ cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const 
   if (aligned_end > g.col_begin) {
     LaunchGeom ga = g;
     ga.col_end = aligned_end;
-    StepConst<double> sc;
-    fill_step<double>(host_consts<double>(dev), ptsphy, &sc);
+    StepConst<T> sc;
+    fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
     const int grid = (aligned_end - g.col_begin) / 32;
     void *args[] = {(void *)&ft, (void *)&tm, (void *)&ga, (void *)&sc};
     e = cudaLaunchKernel(fn, dim3(grid), dim3(32), args, smem, stream);
@@ -760,14 +764,21 @@ cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const 
   if (aligned_end < g.col_end) {
     LaunchGeom gt = g;
     gt.col_begin = aligned_end;
-    e = launch_direct<double>(ft, gt, ptsphy, VARIANT_DIRECT_R168, stream);
+    e = launch_direct<T>(ft, gt, ptsphy, VARIANT_DIRECT_R168, stream);
   }
   return e;
 }
 
-cudaError_t tmap_kernel_info(int out[8]) {
-  const void *fn = (const void *)cloudsc_sweep_tmap<double>;
-  const size_t dyn = TmapIO<double>::kSmem;
+cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
+                              int precision, cudaStream_t stream) {
+  if (precision == CLOUDSC_B200_FP32) return launch_sweep_tmap_t<float>(ft, tm, g, ptsphy, stream);
+  return launch_sweep_tmap_t<double>(ft, tm, g, ptsphy, stream);
+}
+
+template <typename T>
+static cudaError_t tmap_kernel_info_t(int out[8]) {
+  const void *fn = (const void *)cloudsc_sweep_tmap<T>;
+  const size_t dyn = TmapIO<T>::kSmem;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -781,6 +792,10 @@ cudaError_t tmap_kernel_info(int out[8]) {
   out[0] = a.numRegs; out[1] = (int)a.localSizeBytes; out[2] = (int)a.sharedSizeBytes; out[3] = a.maxThreadsPerBlock;
   out[4] = nb; out[5] = 32; out[6] = 100; out[7] = (int)dyn;
   return cudaSuccess;
+}
+
+cudaError_t tmap_kernel_info(int precision, int out[8]) {
+  return precision == CLOUDSC_B200_FP32 ? tmap_kernel_info_t<float>(out) : tmap_kernel_info_t<double>(out);
 }
 
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,

@@ -64,8 +64,8 @@ extern const int kArenaGroupB[3];
 extern const int kArenaGroupC[2];
 
 cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
-                              cudaStream_t stream);
-cudaError_t tmap_kernel_info(int out[8]);
+                              int precision, cudaStream_t stream);
+cudaError_t tmap_kernel_info(int precision, int out[8]);
 
 cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<float> &c32);
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,

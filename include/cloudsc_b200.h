@@ -146,7 +146,7 @@ int cloudsc_b200_release_cache(void);
 typedef struct cloudsc_b200_state cloudsc_b200_state;
 int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc_b200_state **out);
 int cloudsc_b200_destroy(cloudsc_b200_state *st);
-/* H2D of every R/B field (host doubles; converted on the fly for FP32 states) */
+/* H2D of every R/B field (host arrays of the state's element type: double, or float for FP32 states; KTYPE int) */
 int cloudsc_b200_upload(cloudsc_b200_state *st, void *const host_fields[CLOUDSC_NFIELDS], void *stream);
 /* D2H of every W/B field */
 int cloudsc_b200_download(cloudsc_b200_state *st, void *const host_fields[CLOUDSC_NFIELDS], void *stream);

@@ -237,6 +237,45 @@ def test_fp32_build_within_the_stated_single_precision_bars(built, oracle, input
     assert validate.all_pass(errs, "fp32"), "\n" + validate.format_table(errs, "fp32")
 
 
+@pytest.mark.parametrize("ngptot,nproma", [(1000, 128), (4099, 64), (777, 96)])
+def test_fp32_resident_state_within_the_single_precision_bars(built, oracle, input_data, ngptot, nproma):
+    """FP32 resident state (cloudsc_b200_create(..., FP32): float host arrays, float arena, FLOAT32 tensor maps,
+    16 resident warps per SM) against the FP64 oracle within validate.FP32_L1_BARS, incl. a ragged tail; and it
+    agrees with cloudsc_b200_launch(FP32) on the same float fields to rounding-level differences."""
+    import torch
+    from dwarf_p_cloudsc_b200 import api, params, state, validate
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    F = state.blocked_fields(cols, ngptot, nproma, klev)
+    R = {n: a.copy() for n, a in F.items()}
+    oracle.run(R, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 0)
+    api.set_params(p, k)
+    H = {n: (a.astype(np.float32) if a.dtype == np.float64 else a.copy()) for n, a in F.items()}
+    st = api.State(ngptot, nproma, klev, api.FP32)
+    try:
+        info = st.kernel_info()
+        assert info["variant"] == 100 and info["local_bytes"] == 0 and info["blocks_per_sm"] >= 16, info
+        st.upload(H)
+        st.step(scalars["PTSPHY"])
+        st.download(H)
+        st.sync()
+    finally:
+        st.close()
+    G = {n: a.astype(np.float64) if a.dtype == np.float32 else a for n, a in H.items()}
+    for n in state.VALIDATE_ORDER:
+        assert np.isfinite(G[n]).all(), n
+    errs = validate.validate(G, R, ngptot)
+    assert validate.all_pass(errs, "fp32"), "\n" + validate.format_table(errs, "fp32")
+    # same arithmetic through caller-owned float fields
+    D = {n: torch.from_numpy(a.astype(np.float32) if a.dtype == np.float64 else a).cuda() for n, a in F.items()}
+    api.launch(D, ngptot, nproma, klev, scalars["PTSPHY"], precision=api.FP32)
+    torch.cuda.synchronize()
+    for n in state.VALIDATE_ORDER:
+        a = state.unblock(D[n].cpu().numpy(), ngptot)[..., :ngptot]
+        b = state.unblock(H[n], ngptot)[..., :ngptot]
+        assert np.array_equal(a, b), n
+
+
 @pytest.mark.parametrize("kernel_variant", [0, 2, 5, 8, 9])
 def test_no_write_outside_the_fields(built, input_data, kernel_variant):
     """Guard zones around every device field (compute-sanitizer is not available on the pool): 4 KB of a
