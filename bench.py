@@ -331,9 +331,12 @@ def run_b200(args, rank, local_rank, world):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f)
+            traffic = (traffic.get("fp32") or {}).get("dram_bytes_per_launch") if fp32 else traffic.get("dram_bytes_per_launch")
+        if ngptot != 163840:
+            traffic = None                # the ncu capture is of the default workload
     except Exception:
-        pass
+        traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "cloudsc_sweep",
                 "algorithmic_bytes_per_column": bytes_col, "columns_per_launch": ngptot}

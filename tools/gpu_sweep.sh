@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for np in 32 64 128 256; do
   timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --nproma $np > gpurun_out/sweep_fp64_nproma$np.json 2> gpurun_out/sweep_fp64_nproma$np.err
 done
-for np in 128 256; do
+for np in 32 64 128 256; do
   timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --nproma $np --precision fp32 > gpurun_out/sweep_fp32_nproma$np.json 2> gpurun_out/sweep_fp32_nproma$np.err
 done
 timeout -s KILL 900 python bench.py --steps 3 --warmup 3 --no-cpu --ngptot 655360 --e2e-steps 3 > gpurun_out/sweep_e2e_655360.json 2> gpurun_out/sweep_e2e_655360.err
