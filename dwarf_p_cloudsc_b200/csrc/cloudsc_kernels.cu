@@ -740,6 +740,9 @@ template <typename T>
 static cudaError_t launch_sweep_tmap_t(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
                                        cudaStream_t stream) {
   if (g.col_end <= g.col_begin) return cudaSuccess;
+  /* the kernel addresses output rows with 32-bit element offsets (as the bulk-copy kernels, tile_ok()) */
+  const long long nblk = (g.col_end + g.nproma - 1) / g.nproma;
+  if (nblk * 5 * (g.klev + 1) * g.nproma >= (1ll << 32)) return launch_any<T>(ft, g, ptsphy, VARIANT_AUTO, stream);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
