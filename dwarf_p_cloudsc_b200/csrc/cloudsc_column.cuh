@@ -127,6 +127,80 @@ static inline float cs(float x, float y) { return std::copysign(x, y); }
  * below for the two that can run away to -inf (exp(-x^2) of the snow autoconversion, and pow_fast of
  * a vanishing base), where the result underflows harmlessly to 1e-304 instead of 0.
  */
+#ifndef CLOUDSC_EXP_TABLE
+#define CLOUDSC_EXP_TABLE 1
+#endif
+#if CLOUDSC_EXP_TABLE
+/* Table-driven variant (the default): x = (64 n + j) ln2/64 + r, exp x = 2^n 2^(j/64) (1 + expm1 r) with a 64-entry
+ * table of correctly rounded 2^(j/64) and the degree-5 Taylor polynomial on |r| <= ln2/128 (truncation 3.5e-17,
+ * total ~1 ulp).  15 instructions and 8 constants instead of 25 and 16: the FP64 kernel is bound by instruction
+ * supply, so instructions and code bytes are what an exp costs.  On the device the table is
+ * staged in shared memory by every warp before the sweep (exp2_tab_init); a lane reads its entry with one LDS. */
+#define CLOUDSC_EXP2_TAB_VALUES \
+  0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, \
+  0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0, \
+  0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0, \
+  0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0, \
+  0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0, \
+  0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0, \
+  0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0, \
+  0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0, \
+  0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0, \
+  0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0, \
+  0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0, \
+  0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0, \
+  0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0, \
+  0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, \
+  0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0, \
+  0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0 \
+
+#if defined(__CUDACC__)
+static __constant__ double k_exp2_tab_c[64] = {CLOUDSC_EXP2_TAB_VALUES};
+__device__ __forceinline__ double *exp2_tab() {
+  __shared__ double tab[64];
+  return tab;
+}
+/* every warp writes all 64 entries (identical values: no ordering between warps is needed) */
+__device__ __forceinline__ void exp2_tab_init() {
+  const int lane = (int)(threadIdx.x & 31u);
+  double *tab = exp2_tab();
+  tab[lane] = k_exp2_tab_c[lane];
+  tab[lane + 32] = k_exp2_tab_c[lane + 32];
+  __syncwarp();
+}
+#else
+static const double k_exp2_tab_h[64] = {CLOUDSC_EXP2_TAB_VALUES};
+static inline void exp2_tab_init() {}
+#endif
+CLOUDSC_FN double exp_fast(double x) {
+  const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
+  const double t = x * 92.332482616893658 + magic;             /* 64 / ln 2 */
+  const double fn = t - magic;
+  double r = fn * (-6.93147180369123816490e-01 / 64.0) + x;    /* ln2_hi / 64: 21 significant bits, fn < 2^17 */
+  r = fn * (-1.90821492927058770002e-10 / 64.0) + r;
+  double q = r * 8.3333333333333332e-03 + 4.1666666666666664e-02;
+  q = r * q + 1.6666666666666666e-01;
+  q = r * q + 0.5;
+  const double p = (r * r) * q + r;                            /* expm1(r) */
+#if defined(__CUDACC__)
+  const int ti = __double2loint(t);
+  const double tv = exp2_tab()[ti & 63];
+  const double res = tv * p + tv;
+  return __hiloint2double(__double2hiint(res) + ((ti >> 6) << 20), __double2loint(res));
+#else
+  long long tb, pb;
+  std::memcpy(&tb, &t, 8);
+  const int ti = (int)(tb & 0xffffffffLL);
+  const double tv = k_exp2_tab_h[ti & 63];
+  double res = tv * p + tv;
+  std::memcpy(&pb, &res, 8);
+  pb += (long long)(ti >> 6) << 52;
+  std::memcpy(&res, &pb, 8);
+  return res;
+#endif
+}
+#else
+CLOUDSC_FN void exp2_tab_init() {}
 CLOUDSC_FN double exp_fast(double x) {
   const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
   const double t = x * 1.4426950408889634 + magic;
@@ -160,6 +234,7 @@ CLOUDSC_FN double exp_fast(double x) {
   return p;
 #endif
 }
+#endif
 /* Single precision: the special-function unit is accurate to ~2 ulp, which is all a 24-bit result can use.
  * expf() is already branch-free (range reduction + MUFU.EX2); division, sqrt and powf are the library's
  * branchy IEEE sequences (64 slow-path calls in the FP32 kernel), replaced below by MUFU.RCP + one Newton
@@ -275,6 +350,8 @@ CLOUDSC_FN float sqrt_fast(float x) {
 #define CLOUDSC_DIV(a, b) ((a) / (b))
 #define CLOUDSC_DIVR(a, b, r) ((a) / (b))  /* a/b where r == 1/b is available in fast mode */
 #define CLOUDSC_POW(x, y) pw(x, y)
+#define CLOUDSC_EXP_COLD(x) ex_lib(x)
+#define CLOUDSC_EXP_LO_COLD(x) ex_lib(x)
 #define CLOUDSC_SQRT(x) sq(x)
 template <typename T> CLOUDSC_FN T pow15(T x) { return pw(x, T(1.5)); }
 template <typename T> CLOUDSC_FN T cube(T x) { return pw(x, T(3.0)); }
@@ -286,7 +363,28 @@ template <typename T> CLOUDSC_FN T ex_lo(T x) { return ex_lib(x); }
 #define CLOUDSC_RCP(x) rcp_fast(x)
 #define CLOUDSC_DIV(a, b) ((a) * rcp_fast(b))
 #define CLOUDSC_DIVR(a, b, r) ((a) * (r))
+/* CLOUDSC_CALLS: the FP64 pow (log + exp, ~62 instructions, 13 sites) and the exp of the process blocks as ONE
+ * out-of-line copy each.  The loop body of the FP64 kernel (2400 hot instructions = 38 KB) does not fit the SM's
+ * 32 KB instruction cache (ncu: sm__icc_request_hit_rate 83 %, GPC instruction-cache requests at 95 % of peak);
+ * the saturation / Newton exps on the critical path stay inline. */
+#ifndef CLOUDSC_CALLS
+#define CLOUDSC_CALLS 0
+#endif
+#if CLOUDSC_CALLS && defined(__CUDACC__)
+__device__ __noinline__ double pow_call(double x, double y) { return exp_fast_lo(y * log_fast(x)); }
+__device__ __noinline__ double exp_call(double x) { return exp_fast(x); }
+__device__ __noinline__ double exp_lo_call(double x) { return exp_fast_lo(x); }
+CLOUDSC_FN float pow_call(float x, float y) { return pow_fast(x, y); }
+CLOUDSC_FN float exp_call(float x) { return exp_fast(x); }
+CLOUDSC_FN float exp_lo_call(float x) { return exp_fast_lo(x); }
+#define CLOUDSC_POW(x, y) pow_call(x, y)
+#define CLOUDSC_EXP_COLD(x) exp_call(x)
+#define CLOUDSC_EXP_LO_COLD(x) exp_lo_call(x)
+#else
 #define CLOUDSC_POW(x, y) pow_fast(x, y)
+#define CLOUDSC_EXP_COLD(x) exp_fast(x)
+#define CLOUDSC_EXP_LO_COLD(x) exp_fast_lo(x)
+#endif
 #define CLOUDSC_SQRT(x) sqrt_fast(x)
 template <typename T> CLOUDSC_FN T pow15(T x) { return x * sqrt_fast(x); }
 template <typename T> CLOUDSC_FN T cube(T x) { return (x * x) * x; }
@@ -367,6 +465,9 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   const T zero = T(0.0), one = T(1.0);
   const T ptsphy = sc.ptsphy;
   const T zqtmst = sc.zqtmst;
+#if !CLOUDSC_STRICT
+  if (sizeof(T) == 8) exp2_tab_init();
+#endif
   /* wet-bulb fit constants with exact binary64 high words, cloudsc_c.c:268,270 */
   const T ztw3 = T(0.85e5), ztw5 = T(275.0);
 
@@ -739,7 +840,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       if (qxfg[0] > c.rlmin && t < c.rtt) {
         const T vpice = CLOUDSC_DIVR((c.r2es * e_ice) * c.rv, c.rd, c.r_rd);
         const T vpliq = vpice * fokoop;
-        const T icenuclei = T(1000.0) * ex(CLOUDSC_DIV(c.p1296 * (vpliq - vpice), vpliq) - c.p0639);
+        const T icenuclei = T(1000.0) * CLOUDSC_EXP_COLD(CLOUDSC_DIV(c.p1296 * (vpliq - vpice), vpliq) - c.p0639);
 #if CLOUDSC_STRICT
         const T add = (c.rlstt * (c.rlstt / (c.rv * t) - one)) / (c.p0024 * t);
         const T bdd = ((c.rv * t) * pap) / (c.p221 * vpice);
@@ -795,9 +896,9 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* 4.3a autoconversion to snow, :1617-1637 */
       if (t <= c.rtt) {
         if (icecld > c.zepsec) {
-          const T zco = sc.snowlin * ex(c.rsnowlin2 * (t - c.rtt));
+          const T zco = sc.snowlin * CLOUDSC_EXP_COLD(c.rsnowlin2 * (t - c.rtt));
           const T x = CLOUDSC_DIVR(icecld, c.rlcritsnow, c.r_rlcritsnow);
-          const T snowaut = zco * (one - ex_lo(-(x * x)));
+          const T snowaut = zco * (one - CLOUDSC_EXP_LO_COLD(-(x * x)));
           qb13 = qb13 + snowaut;
         }
       }
@@ -865,7 +966,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           if (s.rainfrac > c.p08) {
             const T lambda = CLOUDSC_POW(CLOUDSC_DIV(c.rcl_fac1, rho * qx[2]), c.rcl_fac2);
             const T temp = c.rcl_fzrab * (t - c.rtt);
-            const T frz = ((ptsphy * CLOUDSC_DIVR(c.rcl_const5r, rho, r_rho)) * (ex(temp) - one)) * CLOUDSC_POW(lambda, c.rcl_const6r);
+            const T frz = ((ptsphy * CLOUDSC_DIVR(c.rcl_const5r, rho, r_rho)) * (CLOUDSC_EXP_COLD(temp) - one)) * CLOUDSC_POW(lambda, c.rcl_const6r);
             frzmax = mx(frz, zero);
           } else {
             const T cons1 = ab(CLOUDSC_DIVR(ptsphy * (one + T(0.5) * (c.rtt - t)), c.rtaumel, c.r_rtaumel));
