@@ -133,8 +133,8 @@ static inline float cs(float x, float y) { return std::copysign(x, y); }
 #if CLOUDSC_EXP_TABLE
 /* Table-driven variant (the default): x = (64 n + j) ln2/64 + r, exp x = 2^n 2^(j/64) (1 + expm1 r) with a 64-entry
  * table of correctly rounded 2^(j/64) and the degree-5 Taylor polynomial on |r| <= ln2/128 (truncation 3.5e-17,
- * total ~1 ulp).  15 instructions and 8 constants instead of 25 and 16: the FP64 kernel is bound by instruction
- * supply, so instructions and code bytes are what an exp costs.  On the device the table is
+ * total ~1 ulp).  15 instructions and 8 constants instead of 25 and 16: instruction supply is one of the limits of
+ * the FP64 kernel, so an exp costs its instructions and its code bytes.  On the device the table is
  * staged in shared memory by every warp before the sweep (exp2_tab_init); a lane reads its entry with one LDS. */
 #define CLOUDSC_EXP2_TAB_VALUES \
   0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, \
