@@ -393,7 +393,10 @@ struct TmapIO {
 };
 
 /* resident warps per SM the one-warp-CTA kernels are sized for: 168 registers in FP64 (12 warps), 128 in FP32 (16) */
-template <typename T> constexpr int warps_per_sm() { return sizeof(T) == 4 ? 16 : 12; }
+#ifndef CLOUDSC_F64_WARPS_PER_SM
+#define CLOUDSC_F64_WARPS_PER_SM 12   /* 16 = a 128-register FP64 build (spills; measured slower, profiles/README.md) */
+#endif
+template <typename T> constexpr int warps_per_sm() { return sizeof(T) == 4 ? 16 : CLOUDSC_F64_WARPS_PER_SM; }
 
 template <typename T>
 __global__ void __launch_bounds__(32, warps_per_sm<T>())
