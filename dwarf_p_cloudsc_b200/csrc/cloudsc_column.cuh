@@ -160,13 +160,15 @@ __device__ __forceinline__ double *exp2_tab() {
   __shared__ double tab[64];
   return tab;
 }
-/* every warp writes all 64 entries (identical values: no ordering between warps is needed) */
+/* every warp writes all 64 entries (identical values: no ordering between warps is needed); the entries are dealt
+ * out over the lanes that are actually here, so a partial warp (ragged last block) fills the whole table too */
 __device__ __forceinline__ void exp2_tab_init() {
+  const unsigned m = __activemask();
   const int lane = (int)(threadIdx.x & 31u);
+  const int n = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
   double *tab = exp2_tab();
-  tab[lane] = k_exp2_tab_c[lane];
-  tab[lane + 32] = k_exp2_tab_c[lane + 32];
-  __syncwarp();
+  for (int i = rank; i < 64; i += n) tab[i] = k_exp2_tab_c[i];
+  __syncwarp(m);
 }
 #else
 static const double k_exp2_tab_h[64] = {CLOUDSC_EXP2_TAB_VALUES};
