@@ -396,6 +396,20 @@ template <typename T> CLOUDSC_FN T ex(T x) { return exp_fast(x); }
 template <typename T> CLOUDSC_FN T ex_lo(T x) { return exp_fast_lo(x); }
 #endif
 
+/* Optional per-thread scratch of an IO policy (IO::kScratch slots, `T &scr(int)`): values that live through the whole
+ * sweep but are touched once per level (the six running flux sums) or only in some blocks (per-column constants) are
+ * parked there instead of holding 20 of the 168 registers.  IO policies without scratch keep them in registers. */
+template <typename IO, typename = void> struct io_scratch { static constexpr int value = 0; };
+template <typename IO> struct io_scratch<IO, decltype((void)IO::kScratch)> { static constexpr int value = IO::kScratch; };
+enum { PARK_FSQLF, PARK_FSQIF, PARK_FCQLNG, PARK_FCQNNG, PARK_FSQLTUR, PARK_FSQITUR, PARK_PAPH_SURF, PARK_R_PAPH_SURF,
+       PARK_KK_NUM_POW, PARK_LCRIT_KK, PARK_COUNT };
+template <int I, typename T, typename IO> CLOUDSC_FN T park_ld(IO &io, const T &reg) {
+  if constexpr (io_scratch<IO>::value > I) return io.scr(I); else return reg;
+}
+template <int I, typename T, typename IO> CLOUDSC_FN void park_st(IO &io, T &reg, T v) {
+  if constexpr (io_scratch<IO>::value > I) io.scr(I) = v; else reg = v;
+}
+
 /* State carried from level k-1 to level k (what "k-caching" keeps in registers) */
 template <typename T>
 struct Carry {
@@ -476,15 +490,23 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   const int ktop = c.ncldtop - 1; /* first level (0-based) of the physics sweep, :732 */
 
   /* per-column constants */
-  const T paph_surf = io.paph_row(klev); /* paph[klev+1] :1260,2064 */
-  const T r_paph_surf = CLOUDSC_RCP(paph_surf);
-  (void)r_paph_surf;
+  T paph_surf_r = zero, r_paph_surf_r = zero, kk_num_pow_r = zero, lcrit_kk_r = zero;   /* registers, unless parked */
+  {
+    const T ps = io.paph_row(klev); /* paph[klev+1] :1260,2064 */
+    park_st<PARK_PAPH_SURF>(io, paph_surf_r, ps);
+    park_st<PARK_R_PAPH_SURF>(io, r_paph_surf_r, CLOUDSC_RCP(ps));
+  }
   const T plsm = io.plsm();
   const int ktype = io.ktype();
   /* cloudsc_c.c:1710-1717 */
   const bool land = plsm > T(0.5);
-  const T kk_num_pow = land ? c.kk_num_pow_land : c.kk_num_pow_sea;
-  const T lcrit_kk = land ? c.rclcrit_land : c.rclcrit_sea;
+  park_st<PARK_KK_NUM_POW>(io, kk_num_pow_r, land ? c.kk_num_pow_land : c.kk_num_pow_sea);
+  park_st<PARK_LCRIT_KK>(io, lcrit_kk_r, land ? c.rclcrit_land : c.rclcrit_sea);
+#define paph_surf park_ld<PARK_PAPH_SURF>(io, paph_surf_r)
+#define r_paph_surf park_ld<PARK_R_PAPH_SURF>(io, r_paph_surf_r)
+#define kk_num_pow park_ld<PARK_KK_NUM_POW>(io, kk_num_pow_r)
+#define lcrit_kk park_ld<PARK_LCRIT_KK>(io, lcrit_kk_r)
+  (void)r_paph_surf_r;
 
   Carry<T> s;
   s.tp1_m1 = zero; s.a_m1 = zero; s.pap_m1 = zero;
@@ -494,7 +516,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   s.pf_i = zero; s.pf_r = zero; s.pf_s = zero;               /* :493 */
   s.covptot = zero; s.covpmax = zero; s.cldtopdist = zero;   /* :720-723 */
   s.rainfrac = zero;                                         /* :512 */
-  s.fsqlf = zero; s.fsqif = zero; s.fcqlng = zero; s.fcqnng = zero; s.fsqltur = zero; s.fsqitur = zero;
+  park_st<PARK_FSQLF>(io, s.fsqlf, zero); park_st<PARK_FSQIF>(io, s.fsqif, zero); park_st<PARK_FCQLNG>(io, s.fcqlng, zero);
+  park_st<PARK_FCQNNG>(io, s.fcqnng, zero); park_st<PARK_FSQLTUR>(io, s.fsqltur, zero); park_st<PARK_FSQITUR>(io, s.fsqitur, zero);
 
   /* row 0 of every flux output, :2533-2542 and zpfplsx[.][0]=0 -> :2523-2524,2578-2579 */
   io.template st_row0<OUT_FSQLF>(zero);  io.template st_row0<OUT_FSQIF>(zero);
@@ -1202,21 +1225,27 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T pvfl = io.template ld<IN_PVFL>(k), pvfi = io.template ld<IN_PVFI>(k);
       /* rain/snow rows copy the liquid/ice running sums of the level above (:2550-2555).
        * zlneg[m] (:526,550: the condensate removed by the tidy-up, else 0) == qx0[m] - qx[m] exactly. */
-      const T fsqrf = s.fsqlf + (qxn2d[2] - qx0[2]) * gdph_r;
-      const T fcqrng = s.fcqlng + (qx0[2] - qx[2]) * gdph_r;
-      const T fsqsf = s.fsqif + (qxn2d[3] - qx0[3]) * gdph_r;
-      const T fcqsng = s.fcqnng + (qx0[3] - qx[3]) * gdph_r;
-      s.fsqlf = s.fsqlf + (qxn2d[0] - qx0[0] + pvfl * ptsphy - alfa_w * plude_out) * gdph_r;
-      s.fcqlng = s.fcqlng + (qx0[0] - qx[0]) * gdph_r;
-      s.fsqltur = s.fsqltur + (pvfl * ptsphy) * gdph_r;
-      s.fsqif = s.fsqif + (qxn2d[1] - qx0[1] + pvfi * ptsphy - (one - alfa_w) * plude_out) * gdph_r;
-      s.fcqnng = s.fcqnng + (qx0[1] - qx[1]) * gdph_r;
-      s.fsqitur = s.fsqitur + (pvfi * ptsphy) * gdph_r;
-      io.template st<OUT_FSQLF>(k + 1, s.fsqlf);   io.template st<OUT_FSQIF>(k + 1, s.fsqif);
+      const T o_fsqlf = park_ld<PARK_FSQLF>(io, s.fsqlf), o_fsqif = park_ld<PARK_FSQIF>(io, s.fsqif);
+      const T o_fcqlng = park_ld<PARK_FCQLNG>(io, s.fcqlng), o_fcqnng = park_ld<PARK_FCQNNG>(io, s.fcqnng);
+      const T o_fsqltur = park_ld<PARK_FSQLTUR>(io, s.fsqltur), o_fsqitur = park_ld<PARK_FSQITUR>(io, s.fsqitur);
+      const T fsqrf = o_fsqlf + (qxn2d[2] - qx0[2]) * gdph_r;
+      const T fcqrng = o_fcqlng + (qx0[2] - qx[2]) * gdph_r;
+      const T fsqsf = o_fsqif + (qxn2d[3] - qx0[3]) * gdph_r;
+      const T fcqsng = o_fcqnng + (qx0[3] - qx[3]) * gdph_r;
+      const T n_fsqlf = o_fsqlf + (qxn2d[0] - qx0[0] + pvfl * ptsphy - alfa_w * plude_out) * gdph_r;
+      const T n_fcqlng = o_fcqlng + (qx0[0] - qx[0]) * gdph_r;
+      const T n_fsqltur = o_fsqltur + (pvfl * ptsphy) * gdph_r;
+      const T n_fsqif = o_fsqif + (qxn2d[1] - qx0[1] + pvfi * ptsphy - (one - alfa_w) * plude_out) * gdph_r;
+      const T n_fcqnng = o_fcqnng + (qx0[1] - qx[1]) * gdph_r;
+      const T n_fsqitur = o_fsqitur + (pvfi * ptsphy) * gdph_r;
+      park_st<PARK_FSQLF>(io, s.fsqlf, n_fsqlf); park_st<PARK_FSQIF>(io, s.fsqif, n_fsqif);
+      park_st<PARK_FCQLNG>(io, s.fcqlng, n_fcqlng); park_st<PARK_FCQNNG>(io, s.fcqnng, n_fcqnng);
+      park_st<PARK_FSQLTUR>(io, s.fsqltur, n_fsqltur); park_st<PARK_FSQITUR>(io, s.fsqitur, n_fsqitur);
+      io.template st<OUT_FSQLF>(k + 1, n_fsqlf);   io.template st<OUT_FSQIF>(k + 1, n_fsqif);
       io.template st<OUT_FSQRF>(k + 1, fsqrf);     io.template st<OUT_FSQSF>(k + 1, fsqsf);
-      io.template st<OUT_FCQLNG>(k + 1, s.fcqlng); io.template st<OUT_FCQNNG>(k + 1, s.fcqnng);
+      io.template st<OUT_FCQLNG>(k + 1, n_fcqlng); io.template st<OUT_FCQNNG>(k + 1, n_fcqnng);
       io.template st<OUT_FCQRNG>(k + 1, fcqrng);   io.template st<OUT_FCQSNG>(k + 1, fcqsng);
-      io.template st<OUT_FSQLTUR>(k + 1, s.fsqltur); io.template st<OUT_FSQITUR>(k + 1, s.fsqitur);
+      io.template st<OUT_FSQLTUR>(k + 1, n_fsqltur); io.template st<OUT_FSQITUR>(k + 1, n_fsqitur);
     }
 
     /* ---- shift the level-(k-1) cache */
@@ -1226,6 +1255,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   }
   io.st_rainfrac(s.rainfrac);
 }
+#undef paph_surf
+#undef r_paph_surf
+#undef kk_num_pow
+#undef lcrit_kk
 
 } /* namespace cloudsc */
 #endif

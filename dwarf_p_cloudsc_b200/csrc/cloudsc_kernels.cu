@@ -327,7 +327,8 @@ struct TmapIO {
   static constexpr int kCols = 32;
   static constexpr int kRow = kCols * (int)sizeof(T);
   static constexpr int kStage = N_IN * kRow;
-  static constexpr int kSmem = 2 * kStage + 32;
+  static constexpr int kScratch = PARK_COUNT;              /* rows of per-thread scratch behind the ring (park_ld/park_st) */
+  static constexpr int kSmem = 2 * kStage + 32 + kScratch * kRow;
   const FieldTable &ft;
   const TensorMaps &tm;
   int ibl, jl0;                       /* NPROMA block and first column (inside it) of this warp */
@@ -374,6 +375,9 @@ struct TmapIO {
     }
     cL += (unsigned)stride; cH1 += (unsigned)stride; cC += (unsigned)stride;
     CLOUDSC_TSTAMP(3);
+  }
+  __device__ __forceinline__ T &scr(int i) const {
+    return const_cast<T *>(stage_t)[(2 * kStage + 32) / (int)sizeof(T) + i * kCols];
   }
   template <int S> __device__ __forceinline__ T ld(int) const { return cur[tmap_row(S) * kCols]; }
   template <int S> __device__ __forceinline__ T ld_next(int) const { return cur[tmap_row(S) * kCols]; }
