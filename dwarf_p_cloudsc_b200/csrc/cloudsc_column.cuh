@@ -402,7 +402,7 @@ template <typename T> CLOUDSC_FN T ex_lo(T x) { return exp_fast_lo(x); }
 template <typename IO, typename = void> struct io_scratch { static constexpr int value = 0; };
 template <typename IO> struct io_scratch<IO, decltype((void)IO::kScratch)> { static constexpr int value = IO::kScratch; };
 enum { PARK_FSQLF, PARK_FSQIF, PARK_FCQLNG, PARK_FCQNNG, PARK_FSQLTUR, PARK_FSQITUR, PARK_PAPH_SURF, PARK_R_PAPH_SURF,
-       PARK_KK_NUM_POW, PARK_LCRIT_KK, PARK_COUNT };
+       PARK_PF_I, PARK_PF_R, PARK_PF_S, PARK_COVPTOT, PARK_COVPMAX, PARK_CLDTOPDIST, PARK_RAINFRAC, PARK_COUNT };
 template <int I, typename T, typename IO> CLOUDSC_FN T park_ld(IO &io, const T &reg) {
   if constexpr (io_scratch<IO>::value > I) return io.scr(I); else return reg;
 }
@@ -490,7 +490,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   const int ktop = c.ncldtop - 1; /* first level (0-based) of the physics sweep, :732 */
 
   /* per-column constants */
-  T paph_surf_r = zero, r_paph_surf_r = zero, kk_num_pow_r = zero, lcrit_kk_r = zero;   /* registers, unless parked */
+  T paph_surf_r = zero, r_paph_surf_r = zero;   /* registers, unless parked */
   {
     const T ps = io.paph_row(klev); /* paph[klev+1] :1260,2064 */
     park_st<PARK_PAPH_SURF>(io, paph_surf_r, ps);
@@ -500,12 +500,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   const int ktype = io.ktype();
   /* cloudsc_c.c:1710-1717 */
   const bool land = plsm > T(0.5);
-  park_st<PARK_KK_NUM_POW>(io, kk_num_pow_r, land ? c.kk_num_pow_land : c.kk_num_pow_sea);
-  park_st<PARK_LCRIT_KK>(io, lcrit_kk_r, land ? c.rclcrit_land : c.rclcrit_sea);
 #define paph_surf park_ld<PARK_PAPH_SURF>(io, paph_surf_r)
 #define r_paph_surf park_ld<PARK_R_PAPH_SURF>(io, r_paph_surf_r)
-#define kk_num_pow park_ld<PARK_KK_NUM_POW>(io, kk_num_pow_r)
-#define lcrit_kk park_ld<PARK_LCRIT_KK>(io, lcrit_kk_r)
+#define kk_num_pow (land ? c.kk_num_pow_land : c.kk_num_pow_sea)
+#define lcrit_kk (land ? c.rclcrit_land : c.rclcrit_sea)
   (void)r_paph_surf_r;
 
   Carry<T> s;
@@ -516,6 +514,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   s.pf_i = zero; s.pf_r = zero; s.pf_s = zero;               /* :493 */
   s.covptot = zero; s.covpmax = zero; s.cldtopdist = zero;   /* :720-723 */
   s.rainfrac = zero;                                         /* :512 */
+  /* (parked by IO policies with scratch: loaded where the level first needs them, stored after their last update) */
+  park_st<PARK_PF_I>(io, s.pf_i, zero); park_st<PARK_PF_R>(io, s.pf_r, zero); park_st<PARK_PF_S>(io, s.pf_s, zero);
+  park_st<PARK_COVPTOT>(io, s.covptot, zero); park_st<PARK_COVPMAX>(io, s.covpmax, zero);
+  park_st<PARK_CLDTOPDIST>(io, s.cldtopdist, zero); park_st<PARK_RAINFRAC>(io, s.rainfrac, zero);
   park_st<PARK_FSQLF>(io, s.fsqlf, zero); park_st<PARK_FSQIF>(io, s.fsqif, zero); park_st<PARK_FCQLNG>(io, s.fcqlng, zero);
   park_st<PARK_FCQNNG>(io, s.fcqnng, zero); park_st<PARK_FSQLTUR>(io, s.fsqltur, zero); park_st<PARK_FSQITUR>(io, s.fsqitur, zero);
 
@@ -856,12 +858,14 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       }
 
       /* ================= 3.7 growth of ice by vapour deposition (Rotstayn), :1384-1447 ==== */
+      s.cldtopdist = park_ld<PARK_CLDTOPDIST>(io, s.cldtopdist);
       if (a >= c.rcldtopcf && s.a_m1 < c.rcldtopcf) s.cldtopdist = zero;
 #if CLOUDSC_STRICT
       else s.cldtopdist = s.cldtopdist + dp / (rho * c.rg);
 #else
       else s.cldtopdist = s.cldtopdist + (dp * r_rho) * sc.zrg_r;
 #endif
+      park_st<PARK_CLDTOPDIST>(io, s.cldtopdist, s.cldtopdist);
       if (qxfg[0] > c.rlmin && t < c.rtt) {
         const T vpice = CLOUDSC_DIVR((c.r2es * e_ice) * c.rv, c.rd, c.r_rd);
         const T vpliq = vpice * fokoop;
@@ -895,9 +899,9 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       T qpretot = zero;
       T fallsrce1 = zero, fallsrce2 = zero, fallsrce3 = zero;
       if (k > ktop) {
-        fallsrce1 = s.pf_i * dtgdp; d1 = d1 + fallsrce1; qxfg[1] = qxfg[1] + fallsrce1; qpretot = qpretot + qxfg[1];
-        fallsrce2 = s.pf_r * dtgdp; d2 = d2 + fallsrce2; qxfg[2] = qxfg[2] + fallsrce2; qpretot = qpretot + qxfg[2];
-        fallsrce3 = s.pf_s * dtgdp; d3 = d3 + fallsrce3; qxfg[3] = qxfg[3] + fallsrce3; qpretot = qpretot + qxfg[3];
+        fallsrce1 = park_ld<PARK_PF_I>(io, s.pf_i) * dtgdp; d1 = d1 + fallsrce1; qxfg[1] = qxfg[1] + fallsrce1; qpretot = qpretot + qxfg[1];
+        fallsrce2 = park_ld<PARK_PF_R>(io, s.pf_r) * dtgdp; d2 = d2 + fallsrce2; qxfg[2] = qxfg[2] + fallsrce2; qpretot = qpretot + qxfg[2];
+        fallsrce3 = park_ld<PARK_PF_S>(io, s.pf_s) * dtgdp; d3 = d3 + fallsrce3; qxfg[3] = qxfg[3] + fallsrce3; qpretot = qpretot + qxfg[3];
       }
       const T fallsink1 = dtgdp * (c.rvice * rho);
       const T fallsink2 = dtgdp * (c.rvrain * rho);
@@ -905,6 +909,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 
       /* precipitation cover, max-random overlap, :1595-1609 */
       T covpclr, raincld, snowcld;
+      s.covptot = park_ld<PARK_COVPTOT>(io, s.covptot);
+      s.covpmax = park_ld<PARK_COVPMAX>(io, s.covpmax);
       if (qpretot > c.zepsec) {
         s.covptot = one - CLOUDSC_DIV((one - s.covptot) * (one - mx(a, s.a_m1)), one - mn(s.a_m1, c.one_m_1em6));
         s.covptot = mx(s.covptot, c.rcovpmin);
@@ -984,11 +990,11 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       if (CLOUDSC_RARE(qx[2] > c.zepsec)) {
         if (t <= c.rtt && s.tp1_m1 > c.rtt) {
           const T qpre = mx(qx[3] + qx[2], c.zepsec);
-          s.rainfrac = CLOUDSC_DIV(qx[2], qpre);
+          park_st<PARK_RAINFRAC>(io, s.rainfrac, CLOUDSC_DIV(qx[2], qpre));
         }
         if (t < c.rtt) {
           T frzmax;
-          if (s.rainfrac > c.p08) {
+          if (park_ld<PARK_RAINFRAC>(io, s.rainfrac) > c.p08) {
             const T lambda = CLOUDSC_POW(CLOUDSC_DIV(c.rcl_fac1, rho * qx[2]), c.rcl_fac2);
             const T temp = c.rcl_fzrab * (t - c.rtt);
             const T frz = ((ptsphy * CLOUDSC_DIVR(c.rcl_const5r, rho, r_rho)) * (CLOUDSC_EXP_COLD(temp) - one)) * CLOUDSC_POW(lambda, c.rcl_const6r);
@@ -1183,6 +1189,8 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       pf_r_n = (fallsink2 * qxn[2]) * rdtgdp;
       pf_s_n = (fallsink3 * qxn[3]) * rdtgdp;
       if (pf_s_n + pf_r_n < c.zepsec) s.covptot = zero;
+      park_st<PARK_COVPTOT>(io, s.covptot, s.covptot);
+      park_st<PARK_COVPMAX>(io, s.covpmax, s.covpmax);
 
       /* ================= 6. tendencies, :2456-2506 ======================================== */
       {
@@ -1250,10 +1258,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 
     /* ---- shift the level-(k-1) cache */
     s.tp1_m1 = t; s.a_m1 = a; s.pap_m1 = pap; s.paph_k = paph_n; s.mf_k = mf_n;
-    s.pf_i = pf_i_n; s.pf_r = pf_r_n; s.pf_s = pf_s_n;
+    park_st<PARK_PF_I>(io, s.pf_i, pf_i_n); park_st<PARK_PF_R>(io, s.pf_r, pf_r_n); park_st<PARK_PF_S>(io, s.pf_s, pf_s_n);
     io.level_end(k);
   }
-  io.st_rainfrac(s.rainfrac);
+  io.st_rainfrac(park_ld<PARK_RAINFRAC>(io, s.rainfrac));
 }
 #undef paph_surf
 #undef r_paph_surf

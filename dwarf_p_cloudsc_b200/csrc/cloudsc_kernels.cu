@@ -179,7 +179,8 @@ struct TileIO {
   static constexpr int kCols = 32 * WARPS;                 /* columns of the CTA tile */
   static constexpr int kRow = kCols * (int)sizeof(T);      /* bytes of one staged row */
   static constexpr int kStage = N_IN * kRow;               /* one input stage */
-  static constexpr int kSmem = 2 * kStage + 32;            /* + full[2], empty[2] mbarriers */
+  static constexpr int kScratch = PARK_COUNT;              /* rows of per-thread scratch behind the ring (park_ld/park_st) */
+  static constexpr int kSmem = 2 * kStage + 32 + kScratch * kRow;   /* ring + full[2], empty[2] mbarriers + scratch */
   const FieldTable &ft;
   /* CTA-uniform: element offsets of (block, level 0, first column of the tile) per field kind */
   long long tileL, tileH, tileC;
@@ -227,6 +228,9 @@ struct TileIO {
       __syncwarp();
     }
     cL += (unsigned)stride; cH1 += (unsigned)stride; cC += (unsigned)stride;
+  }
+  __device__ __forceinline__ T &scr(int i) const {
+    return const_cast<T *>(stage_t)[(2 * kStage + 32) / (int)sizeof(T) + i * kCols];
   }
   template <int S> __device__ __forceinline__ T ld(int) const { return cur[S * kCols]; }
   template <int S> __device__ __forceinline__ T ld_next(int) const { return cur[S * kCols]; }
