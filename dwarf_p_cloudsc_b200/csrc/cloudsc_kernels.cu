@@ -195,6 +195,9 @@ struct TileIO {
      fewer than 2^32 elements): base + offset is one IMAD.WIDE.U32 per store.  cH1 is row k+1 of the
      [klev+1] flux fields, which is what level k writes. */
   unsigned cL, cH1, cC, spstride;
+  /* false for the lanes of the last tile that lie beyond col_end (ragged NGPTOT): they run the sweep on the padding
+     columns of the last NPROMA block -- the same kernel, hence the same rounding, for every column -- but never store */
+  bool live;
 
   __device__ __forceinline__ void issue(int level) {   /* thread 0 only */
     const unsigned st = (unsigned)level & 1u;
@@ -239,15 +242,15 @@ struct TileIO {
   }
   template <int S> __device__ __forceinline__ void st(int, T v) {
     const unsigned off = out_kind(S) == 0 ? cL : out_kind(S) == 1 ? cH1 : cC + (unsigned)out_species(S) * spstride;
-    __stcs(static_cast<T *>(ft.p[out_field(S)]) + off, v);
+    if (live) __stcs(static_cast<T *>(ft.p[out_field(S)]) + off, v);
   }
   /* row 0 of a flux field, before the level loop (cH1 still points at row 1) */
   template <int S> __device__ __forceinline__ void st_row0(T v) {
-    __stcs(static_cast<T *>(ft.p[out_field(S)]) + (cH1 - (unsigned)stride), v);
+    if (live) __stcs(static_cast<T *>(ft.p[out_field(S)]) + (cH1 - (unsigned)stride), v);
   }
   __device__ __forceinline__ T plsm() const { return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PLSM]) + off1); }
   __device__ __forceinline__ int ktype() const { return __ldg(static_cast<const int *>(ft.p[CLOUDSC_F_KTYPE]) + off1); }
-  __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
+  __device__ __forceinline__ void st_rainfrac(T v) { if (live) static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
 };
 
 template <typename T, int WARPS, int MINB>
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 cloudsc_sweep_tile(const __grid_constant__ FieldTable ft, const LaunchGeom g, const __grid_constant__ StepConst<T> sc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using IO = TileIO<T, WARPS>;
-  /* first column of this CTA; col_begin, col_end and nproma are multiples of 32*WARPS (launcher) */
+  /* first column of this CTA; col_begin and nproma are multiples of 32*WARPS (launcher); col_end may be ragged */
   const int ccol = g.col_begin + blockIdx.x * IO::kCols;
   if (ccol >= g.col_end) return;  /* CTA-uniform */
   const int ibl = ccol / g.nproma;
@@ -267,7 +270,8 @@ cloudsc_sweep_tile(const __grid_constant__ FieldTable ft, const LaunchGeom g, co
         smem_u32(smem_raw), smem_u32(smem_raw + 2 * IO::kStage),
         reinterpret_cast<const T *>(smem_raw) + threadIdx.x,
         nullptr, bH + jl, (long long)ibl * g.nproma + jl,
-        (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma)};
+        (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma),
+        ccol + (int)threadIdx.x < g.col_end};
   if (threadIdx.x == 0) {
     mbar_init(io.bar0, 1);
     mbar_init(io.bar0 + 8, 1);
@@ -342,6 +346,7 @@ struct TmapIO {
   const T *cur;
   long long offH, off1;
   unsigned cL, cH1, cC, spstride;     /* 32-bit element offsets of the current level's output rows */
+  bool live;                          /* see TileIO::live */
 
   __device__ __forceinline__ void issue(int level) {   /* one elected lane */
     const unsigned st = (unsigned)level & 1u;
@@ -390,14 +395,14 @@ struct TmapIO {
   }
   template <int S> __device__ __forceinline__ void st(int, T v) {
     const unsigned off = out_kind(S) == 0 ? cL : out_kind(S) == 1 ? cH1 : cC + (unsigned)out_species(S) * spstride;
-    __stcs(static_cast<T *>(ft.p[out_field(S)]) + off, v);
+    if (live) __stcs(static_cast<T *>(ft.p[out_field(S)]) + off, v);
   }
   template <int S> __device__ __forceinline__ void st_row0(T v) {
-    __stcs(static_cast<T *>(ft.p[out_field(S)]) + (cH1 - (unsigned)stride), v);
+    if (live) __stcs(static_cast<T *>(ft.p[out_field(S)]) + (cH1 - (unsigned)stride), v);
   }
   __device__ __forceinline__ T plsm() const { return __ldg(static_cast<const T *>(ft.p[CLOUDSC_F_PLSM]) + off1); }
   __device__ __forceinline__ int ktype() const { return __ldg(static_cast<const int *>(ft.p[CLOUDSC_F_KTYPE]) + off1); }
-  __device__ __forceinline__ void st_rainfrac(T v) { static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
+  __device__ __forceinline__ void st_rainfrac(T v) { if (live) static_cast<T *>(ft.p[CLOUDSC_F_PRAINFRAC_TOPRFZ])[off1] = v; }
 };
 
 /* resident warps per SM the one-warp-CTA kernels are sized for: 168 registers in FP64 (12 warps), 128 in FP32 (16) */
@@ -412,7 +417,7 @@ cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant_
                    const __grid_constant__ StepConst<T> sc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using IO = TmapIO<T>;
-  const int ccol = g.col_begin + blockIdx.x * IO::kCols;   /* col_begin, col_end, nproma: multiples of 32 (launcher) */
+  const int ccol = g.col_begin + blockIdx.x * IO::kCols;   /* col_begin, nproma: multiples of 32 (launcher); col_end may be ragged */
   if (ccol >= g.col_end) return;
   const int ibl = ccol / g.nproma;
   const int jl0 = ccol - ibl * g.nproma;
@@ -422,7 +427,8 @@ cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant_
         smem_u32(smem_raw), smem_u32(smem_raw + 2 * IO::kStage),
         reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
         bH + jl, (long long)ibl * g.nproma + jl,
-        (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma)};
+        (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma),
+        ccol + (int)threadIdx.x < g.col_end};
   if (threadIdx.x == 0) {
     mbar_init(io.bar0, 1);
     mbar_init(io.bar0 + 8, 1);
@@ -724,23 +730,9 @@ static cudaError_t launch_any(const FieldTable &ft, const LaunchGeom &g, double 
   if (is_pipe(variant)) return launch_pipe<T>(ft, g, ptsphy, variant, stream);
   const TileCfg cfg = tile_cfg(variant, g.nproma);
   if (is_tile(variant) && tile_ok<T>(ft, g, cfg)) {
-    /* the TMA kernel moves whole rows of 32*WARPS columns: give it the aligned part of the range and
-       finish a ragged tail with the direct kernel */
-    const int per_cta = 32 * cfg.warps;
-    const int aligned_end = g.col_end - (g.col_end - g.col_begin) % per_cta;
-    cudaError_t e = cudaSuccess;
-    if (aligned_end > g.col_begin) {
-      LaunchGeom ga = g;
-      ga.col_end = aligned_end;
-      e = launch_tile<T>(ft, ga, ptsphy, cfg, stream);
-      if (e != cudaSuccess) return e;
-    }
-    if (aligned_end < g.col_end) {
-      LaunchGeom gt = g;
-      gt.col_begin = aligned_end;
-      e = launch_direct<T>(ft, gt, ptsphy, VARIANT_DIRECT_R168, stream);
-    }
-    return e;
+    /* the TMA kernel moves whole rows of 32*WARPS columns; a ragged last tile reads the padding columns of the last
+       NPROMA block (the fields are [nblocks][..][nproma], so they exist) and masks its stores */
+    return launch_tile<T>(ft, g, ptsphy, cfg, stream);
   }
   /* geometry the TMA path cannot take (NPROMA not a multiple of 32, unaligned column range or
      pointers): same arithmetic, plain global loads */
@@ -763,24 +755,12 @@ static cudaError_t launch_sweep_tmap_t(const FieldTable &ft, const TensorMaps &t
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  /* whole 32-column rows through TMA; a ragged tail (< 32 columns) goes to the plain-load kernel */
-  const int aligned_end = g.col_end - (g.col_end - g.col_begin) % 32;
-  if (aligned_end > g.col_begin) {
-    LaunchGeom ga = g;
-    ga.col_end = aligned_end;
-    StepConst<T> sc;
-    fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
-    const int grid = (aligned_end - g.col_begin) / 32;
-    void *args[] = {(void *)&ft, (void *)&tm, (void *)&ga, (void *)&sc};
-    e = cudaLaunchKernel(fn, dim3(grid), dim3(32), args, smem, stream);
-    if (e != cudaSuccess) return e;
-  }
-  if (aligned_end < g.col_end) {
-    LaunchGeom gt = g;
-    gt.col_begin = aligned_end;
-    e = launch_direct<T>(ft, gt, ptsphy, VARIANT_DIRECT_R168, stream);
-  }
-  return e;
+  /* whole 32-column rows through TMA; the lanes of a ragged last tile beyond col_end mask their stores */
+  StepConst<T> sc;
+  fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
+  const int grid = (g.col_end - g.col_begin + 31) / 32;
+  void *args[] = {(void *)&ft, (void *)&tm, (void *)&g, (void *)&sc};
+  return cudaLaunchKernel(fn, dim3(grid), dim3(32), args, smem, stream);
 }
 
 cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
