@@ -57,7 +57,16 @@ struct HostIO {
   void level_end(int) {}
 };
 
+/* The same policy with per-thread scratch, as the TMA kernels have it: cloudsc_column() then takes its "parked" code
+ * path (flux sums, precipitation carry, per-column constants through IO::scr instead of registers). */
 template <typename T>
+struct HostIOScratch : HostIO<T> {
+  static constexpr int kScratch = PARK_COUNT;
+  T slots[PARK_COUNT];
+  T &scr(int i) { return slots[i]; }
+};
+
+template <typename T, bool PARKED = false>
 int run(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
         int ngptot, int nproma, int klev, double ptsphy) {
   if (check_params(p)) return CLOUDSC_B200_EPARAMS;
@@ -76,8 +85,15 @@ int run(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fiel
     }
     const int bsize = (ngptot - b * nproma) < nproma ? (ngptot - b * nproma) : nproma;
     for (int jl = 0; jl < bsize; jl++) {
-      HostIO<T> io{pb, jl, nproma, klev};
-      cloudsc_column<T>(c, sc, io, klev);
+      if (PARKED) {
+        HostIOScratch<T> io;
+        io.f = pb; io.jl = jl; io.stride = nproma; io.klev = klev;
+        for (int i = 0; i < PARK_COUNT; i++) io.slots[i] = T(-1.0e300);   /* poison: every slot must be written first */
+        cloudsc_column<T>(c, sc, io, klev);
+      } else {
+        HostIO<T> io{pb, jl, nproma, klev};
+        cloudsc_column<T>(c, sc, io, klev);
+      }
     }
   }
   return 0;
@@ -103,6 +119,10 @@ size_t cloudsc_b200_field_block_elems(int f, int nproma, int klev) {
 int cloudsc_emul_blocks_f64(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
                             int ngptot, int nproma, int klev, double ptsphy) {
   return run<double>(p, k, fields, ngptot, nproma, klev, ptsphy);
+}
+int cloudsc_emul_blocks_parked_f64(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
+                                   int ngptot, int nproma, int klev, double ptsphy) {
+  return run<double, true>(p, k, fields, ngptot, nproma, klev, ptsphy);
 }
 int cloudsc_emul_blocks_f32(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
                             int ngptot, int nproma, int klev, double ptsphy) {

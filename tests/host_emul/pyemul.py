@@ -13,13 +13,15 @@ class Emul:
         kernels' arithmetic mode (shared reciprocals, polynomial exp)."""
         name = "libcloudsc_emul_fast.so" if fast else "libcloudsc_emul.so"
         self.lib = ctypes.CDLL(os.path.join(HERE, name), mode=ctypes.RTLD_LOCAL)
-        for n in ("cloudsc_emul_blocks_f64", "cloudsc_emul_blocks_f32"):
+        for n in ("cloudsc_emul_blocks_f64", "cloudsc_emul_blocks_f32", "cloudsc_emul_blocks_parked_f64"):
             fn = getattr(self.lib, n)
             fn.restype = ctypes.c_int
             fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
                            ctypes.c_int, ctypes.c_int, ctypes.c_double]
 
-    def run(self, fields, p, k, ngptot, nproma, klev, ptsphy, dtype=np.float64):
+    def run(self, fields, p, k, ngptot, nproma, klev, ptsphy, dtype=np.float64, parked=False):
+        """parked=True: the IO policy has per-thread scratch, so the column code runs the code path of the TMA kernels
+        (long-lived state through IO::scr)."""
         from dwarf_p_cloudsc_b200.params import FIELDS
         tab = (ctypes.c_void_p * len(FIELDS))()
         for f in FIELDS:
@@ -29,6 +31,9 @@ class Emul:
             assert a.flags["C_CONTIGUOUS"] and a.dtype == (np.int32 if f.kind == "I" else dtype), f.name
             tab[f.index] = a.ctypes.data
         fn = self.lib.cloudsc_emul_blocks_f64 if dtype == np.float64 else self.lib.cloudsc_emul_blocks_f32
+        if parked:
+            assert dtype == np.float64
+            fn = self.lib.cloudsc_emul_blocks_parked_f64
         rc = fn(ctypes.addressof(p), ctypes.addressof(k), tab, ngptot, nproma, klev, ptsphy)
         if rc:
             raise RuntimeError(f"emulation returned {rc}")

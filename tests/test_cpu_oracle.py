@@ -93,6 +93,32 @@ def test_device_column_code_host_build_is_bit_identical(built, oracle, input_dat
         assert np.array_equal(a, b), (variant, f.name, float(np.abs(a - b).max()))
 
 
+@pytest.mark.parametrize("variant", ["", "warm+land+conv+rain+moist+tend", "hot+rain+moist+conv", "sparse"])
+@pytest.mark.parametrize("fast", [False, True])
+def test_parked_state_code_path_is_value_identical(built, oracle, input_data, variant, fast):
+    """The TMA kernels keep long-lived sweep state (flux sums, precipitation carry, per-column constants) in per-thread
+    scratch of the IO policy instead of registers.  Host build of that code path (scratch poisoned before every column):
+    strict mode bit-identical to the reference, fast mode bit-identical to the register path of the same build."""
+    import pyemul
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    c2 = state.perturb(cols, variant)
+    ngptot, nproma = 100, 16
+    A = state.blocked_fields(c2, ngptot, nproma, klev)
+    B = {n: a.copy() for n, a in A.items()}
+    em = pyemul.Emul(fast=fast)
+    if fast:
+        em.run(A, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
+    else:
+        oracle.run(A, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+    em.run(B, p, k, ngptot, nproma, klev, scalars["PTSPHY"], parked=True)
+    for f in params.OUTPUT_FIELDS:
+        a, b = state.unblock(A[f.name], ngptot), state.unblock(B[f.name], ngptot)
+        assert np.isfinite(b).all(), f.name
+        assert np.array_equal(a, b), (variant, f.name, float(np.abs(a - b).max()))
+
+
 def test_perturbations_reach_the_cold_branches(built, oracle, input_data):
     """The synthetic variants must actually exercise what the shipped data leaves cold."""
     from dwarf_p_cloudsc_b200 import params, state
