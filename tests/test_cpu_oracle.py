@@ -119,6 +119,38 @@ def test_parked_state_code_path_is_value_identical(built, oracle, input_data, va
         assert np.array_equal(a, b), (variant, f.name, float(np.abs(a - b).max()))
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 5, 8, 13, 21, 34])
+def test_seed_sweep_of_the_perturbed_inputs(built, oracle, input_data, seed):
+    """Eight more draws of the two busiest synthetic input sets: reference build == plain-C port == host build of the
+    device column code (register path and parked path), bit for bit."""
+    import pyemul
+    import pyoracle
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    ngptot, nproma = 100, 32
+    em = pyemul.Emul()
+    port = pyoracle.PortOracle()
+    for variant in ("warm+land+conv+rain+moist+tend", "sparse+hot+rain+tend"):
+        c2 = state.perturb(cols, variant, seed=seed)
+        A = state.blocked_fields(c2, ngptot, nproma, klev)
+        runs = []
+        for how in ("ref", "port", "emul", "parked"):
+            B = {n: a.copy() for n, a in A.items()}
+            if how == "ref":
+                oracle.run(B, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+            elif how == "port":
+                port.run(B, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+            else:
+                em.run(B, p, k, ngptot, nproma, klev, scalars["PTSPHY"], parked=(how == "parked"))
+            runs.append(B)
+        for f in params.OUTPUT_FIELDS:
+            ref = state.unblock(runs[0][f.name], ngptot)
+            assert np.isfinite(ref).all(), (variant, f.name)
+            for how, B in zip(("port", "emul", "parked"), runs[1:]):
+                assert np.array_equal(ref, state.unblock(B[f.name], ngptot)), (variant, seed, how, f.name)
+
+
 def test_perturbations_reach_the_cold_branches(built, oracle, input_data):
     """The synthetic variants must actually exercise what the shipped data leaves cold."""
     from dwarf_p_cloudsc_b200 import params, state
