@@ -151,6 +151,29 @@ def test_seed_sweep_of_the_perturbed_inputs(built, oracle, input_data, seed):
                 assert np.array_equal(ref, state.unblock(B[f.name], ngptot)), (variant, seed, how, f.name)
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_fast_arithmetic_mode_stays_inside_the_fp64_tolerance(built, oracle, input_data, variant):
+    """CLOUDSC_STRICT=0 is the arithmetic of the product kernels: shared reciprocals, table-driven exp, atanh-series log,
+    pow = exp(y log x), one-reciprocal Newton step, lazy evaluation of what is not read.  Its host build (libm division
+    and sqrt in place of the MUFU seeds + Newton steps, no FMA contraction) must stay inside the per-field FP64
+    tolerance of the GPU parity tests on every synthetic input set, three draws each."""
+    import pyemul
+    from dwarf_p_cloudsc_b200 import params, state, validate
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    ngptot, nproma = 100, 32
+    em = pyemul.Emul(fast=True)
+    for seed in (1234, 7, 99):
+        c2 = state.perturb(cols, variant, seed=seed)
+        R = state.blocked_fields(c2, ngptot, nproma, klev)
+        G = {n: a.copy() for n, a in R.items()}
+        oracle.run(R, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+        em.run(G, p, k, ngptot, nproma, klev, scalars["PTSPHY"], parked=True)
+        errs = validate.validate(G, R, ngptot)
+        assert validate.all_pass(errs), (variant, seed, "\n" + validate.format_table(errs))
+        assert max(e.rel_l1 for e in errs) < 1e-12, (variant, seed, max(e.rel_l1 for e in errs))   # measured <= 3.1e-14
+
+
 def test_perturbations_reach_the_cold_branches(built, oracle, input_data):
     """The synthetic variants must actually exercise what the shipped data leaves cold."""
     from dwarf_p_cloudsc_b200 import params, state
