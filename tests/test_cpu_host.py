@@ -127,3 +127,46 @@ def test_driver_executable_fails_loudly_without_a_gpu(built):
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
     r = subprocess.run([exe, "1", "2"], cwd=GOLDEN, capture_output=True, text=True)
     assert r.returncode != 0 and "right number of arguments" in r.stdout
+
+
+def test_c_and_python_h5lite_agree_on_random_files(hostlib, tmp_path):
+    """Property test (hypothesis): files written by the Python subset writer with a random number of datasets
+    (1..90: one or several symbol-table nodes), random ranks/shapes and the four element types of input.h5 /
+    reference.h5 read back identically through the Python reader and the C reader of the host driver."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from dwarf_p_cloudsc_b200 import h5lite
+
+    dtypes = [np.float64, np.float32, np.int32, np.int64]
+    shapes = st.lists(st.integers(1, 6), min_size=1, max_size=3).map(tuple)
+    counter = [0]
+
+    @settings(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(n=st.integers(1, 90), seed=st.integers(0, 2 ** 31 - 1), shape_list=st.lists(shapes, min_size=1, max_size=8),
+           dt_list=st.lists(st.sampled_from(range(4)), min_size=1, max_size=8))
+    def check(n, seed, shape_list, dt_list):
+        rng = np.random.default_rng(seed)
+        ds = {}
+        for i in range(n):
+            shp = shape_list[i % len(shape_list)]
+            dt = dtypes[dt_list[i % len(dt_list)]]
+            a = (rng.standard_normal(shp) * 1e3) if np.issubdtype(dt, np.floating) else rng.integers(-2 ** 30, 2 ** 30, shp)
+            ds[f"{'FIELD' if i % 3 else 'x'}_{i:03d}"] = np.ascontiguousarray(a.astype(dt))
+        counter[0] += 1
+        path = str(tmp_path / f"r{counter[0]}.h5")
+        h5lite.write_h5(path, ds)
+        back = h5lite.read_h5(path)
+        assert set(back) == set(ds)
+        f = hostlib.h5lite_open(path.encode())
+        assert f, hostlib.h5lite_error()
+        try:
+            assert hostlib.h5lite_count(f) == n
+            for name, a in ds.items():
+                assert back[name].dtype == a.dtype and np.array_equal(back[name], a), name
+                out = np.empty(a.size, dtype=np.float64)
+                assert hostlib.h5lite_read_double(f, name.encode(), out.ctypes.data_as(_dp), a.size) == 0, (name, hostlib.h5lite_error())
+                assert np.array_equal(out, a.reshape(-1).astype(np.float64)), name
+        finally:
+            hostlib.h5lite_close(f)
+        os.remove(path)
+
+    check()
