@@ -53,6 +53,7 @@ lib.cloudsc_b200_set_params.argtypes = [ctypes.POINTER(TECLDP), ctypes.POINTER(C
 lib.cloudsc_b200_launch.argtypes = [_FT, _i, _i, _i, _d, _i, _vp]
 lib.cloudsc_b200_kernel_info.argtypes = [_i, _i, ctypes.POINTER(ctypes.c_int * 8)]
 lib.cloudsc_b200_run_host.argtypes = [_FT, _i, _i, _i, _d, _i, _i, ctypes.POINTER(ctypes.c_double * 4)]
+lib.cloudsc_b200_run_host_ex.argtypes = [_FT, _i, _i, _i, _d, _i, _i, _i, ctypes.POINTER(ctypes.c_double * 4)]
 lib.cloudsc_b200_create.argtypes = [_i, _i, _i, _i, ctypes.POINTER(_vp)]
 lib.cloudsc_b200_destroy.argtypes = [_vp]
 lib.cloudsc_b200_upload.argtypes = [_vp, _FT, _vp]
@@ -66,7 +67,8 @@ lib.cloudsc_b200_set_variant.argtypes = [_i]
 lib.cloudsc_b200_state_kernel_info.argtypes = [_vp, ctypes.POINTER(ctypes.c_int * 8)]
 lib.cloudsc_b200_state_kernel_info.restype = _i
 lib.cloudsc_c.argtypes = [_i, _i, _i, _i, _d] + [_vp] * NFIELDS
-for _n in ("set_params", "launch", "kernel_info", "run_host", "create", "destroy", "upload", "download",
+lib.cloudsc_b200_launch_counts.argtypes = [ctypes.POINTER(ctypes.c_longlong * 5)]
+for _n in ("set_params", "launch", "kernel_info", "launch_counts", "run_host", "run_host_ex", "release_thread", "release_cache", "create", "destroy", "upload", "download",
            "step", "reset_inout", "sync", "set_variant", "get_variant", "device_count",
            "set_params_from_globals"):
     getattr(lib, "cloudsc_b200_" + _n).restype = _i
@@ -126,12 +128,37 @@ def launch_table(tab, ngptot, nproma, klev, ptsphy, precision=FP64, stream=0) ->
 
 
 def run_host(host_fields: Mapping[str, object], ngptot: int, nproma: int, klev: int, ptsphy: float,
-             chunk_blocks: int = 0, nstreams: int = 0) -> Dict[str, float]:
-    """End-to-end run on HOST arrays (pinned preferred): chunked H2D || kernel || D2H pipeline."""
+             chunk_blocks: int = 0, nstreams: int = 0, precision: int = FP64) -> Dict[str, float]:
+    """End-to-end run on HOST arrays (pinned preferred): chunked H2D || kernel || D2H pipeline.
+    precision=FP32: float host arrays, single-precision device arithmetic (cloudsc_b200_run_host_ex)."""
     stats = (ctypes.c_double * 4)()
-    _check(lib.cloudsc_b200_run_host(field_table(host_fields), ngptot, nproma, klev, ptsphy,
-                                     chunk_blocks, nstreams, ctypes.byref(stats)))
+    if precision == FP64:
+        _check(lib.cloudsc_b200_run_host(field_table(host_fields), ngptot, nproma, klev, ptsphy,
+                                         chunk_blocks, nstreams, ctypes.byref(stats)))
+    else:
+        _check(lib.cloudsc_b200_run_host_ex(field_table(host_fields), ngptot, nproma, klev, ptsphy, precision,
+                                            chunk_blocks, nstreams, ctypes.byref(stats)))
     return {"h2d_bytes": stats[0], "d2h_bytes": stats[1], "kernel_ms": stats[2], "wall_ms": stats[3]}
+
+
+KERNEL_FAMILIES = ("tmap", "tile", "direct", "pipe", "direct_aer")
+
+
+def launch_counts() -> Dict[str, int]:
+    """Kernels launched by this process so far, per kernel family (cloudsc_b200_launch_counts)."""
+    out = (ctypes.c_longlong * 5)()
+    _check(lib.cloudsc_b200_launch_counts(out))
+    return dict(zip(KERNEL_FAMILIES, (int(x) for x in out)))
+
+
+def release_cache() -> None:
+    """Free the streams and staging arenas run_host keeps between calls (every device)."""
+    _check(lib.cloudsc_b200_release_cache())
+
+
+def release_thread() -> None:
+    """Free the calling thread's cloudsc_c() staging buffers."""
+    _check(lib.cloudsc_b200_release_thread())
 
 
 def kernel_info(nproma: int = 128, precision: int = FP64) -> Dict[str, int]:

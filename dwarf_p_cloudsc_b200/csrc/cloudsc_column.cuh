@@ -82,6 +82,9 @@ enum OutSlot {
   N_OUT
 };
 
+/* aerosol inputs, read only by the AER instantiation of cloudsc_column() and only where the matching flag is set */
+enum AerSlot { AER_RE_ICE, AER_ICRIT, AER_NICE };
+
 /* ---- math wrappers: same names for double/float, host/device -------------------------------- */
 /* max/min as compare+select.  For the NaN-free values of this scheme they return what
  * fmax/fmin return (zeros of either sign compare equal), at 3 instead of 7 instructions on
@@ -475,8 +478,10 @@ CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
  *   template<int S> void st_row0(T v);        row 0 of a flux field (before the level loop)
  *   T plsm() const; int ktype() const; void st_rainfrac(T);
  *   void level_begin(int k); void level_end(int k);   hooks for staged IO (may be empty)
+ * and, only when instantiated with AER = true (yrecldp->laericesed / laericeauto, cloudsc_c.c:1561-1566,1625-1632):
+ *   template<int A> T ld_aer(int k) const;    aerosol input A (AerSlot) at level k
  */
-template <typename T, typename IO>
+template <typename T, bool AER = false, typename IO>
 CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc, IO &io, const int klev) {
   const T zero = T(0.0), one = T(1.0);
   const T ptsphy = sc.ptsphy;
@@ -903,7 +908,12 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         fallsrce2 = park_ld<PARK_PF_R>(io, s.pf_r) * dtgdp; d2 = d2 + fallsrce2; qxfg[2] = qxfg[2] + fallsrce2; qpretot = qpretot + qxfg[2];
         fallsrce3 = park_ld<PARK_PF_S>(io, s.pf_s) * dtgdp; d3 = d3 + fallsrce3; qxfg[3] = qxfg[3] + fallsrce3; qpretot = qpretot + qxfg[3];
       }
-      const T fallsink1 = dtgdp * (c.rvice * rho);
+      /* aerosol override of the ice fall speed, :1561-1566: zvqx[ice] = 0.002*pow(pre_ice, 1.0) (pow(x, 1) == x).  The
+       * reference overwrites the shared zvqx[1] inside its jl loop, but reads it back for the same jl on the next line
+       * and nowhere else during the sweep (:447 runs before it), so nothing leaks between columns. */
+      T vice = c.rvice;
+      if constexpr (AER) { if (c.laericesed) vice = c.p0002 * io.template ld_aer<AER_RE_ICE>(k); }
+      const T fallsink1 = dtgdp * (vice * rho);
       const T fallsink2 = dtgdp * (c.rvrain * rho);
       const T fallsink3 = dtgdp * (c.rvsnow * rho);
 
@@ -927,8 +937,14 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* 4.3a autoconversion to snow, :1617-1637 */
       if (t <= c.rtt) {
         if (icecld > c.zepsec) {
-          const T zco = sc.snowlin * CLOUDSC_EXP_COLD(c.rsnowlin2 * (t - c.rtt));
-          const T x = CLOUDSC_DIVR(icecld, c.rlcritsnow, c.r_rlcritsnow);
+          T zco = sc.snowlin * CLOUDSC_EXP_COLD(c.rsnowlin2 * (t - c.rtt));
+          T x = CLOUDSC_DIVR(icecld, c.rlcritsnow, c.r_rlcritsnow);
+          if constexpr (AER) {
+            if (c.laericeauto) {   /* :1625-1632: critical ice content and rate scaled by the ice-nuclei concentration */
+              zco = zco * CLOUDSC_POW(CLOUDSC_DIV(c.rnice, io.template ld_aer<AER_NICE>(k)), c.p0333);
+              x = CLOUDSC_DIV(icecld, io.template ld_aer<AER_ICRIT>(k));
+            }
+          }
           const T snowaut = zco * (one - CLOUDSC_EXP_LO_COLD(-(x * x)));
           qb13 = qb13 + snowaut;
         }

@@ -24,7 +24,8 @@
   X(rdepliqrefdepth) X(rcl_kkaac) X(rcl_kkbac) X(rcl_kkaau) X(rcl_kkbauq) X(rcl_kkbaun) \
   X(rcl_kk_cloud_num_sea) X(rcl_kk_cloud_num_land) X(rcl_const1s) X(rcl_const7s) X(rcl_const8s) \
   X(rdensref) X(rcl_cdenom1) X(rcl_cdenom2) X(rcl_cdenom3) X(rcl_const1r) X(rcl_const2r) \
-  X(rcl_const3r) X(rcl_const4r) X(rcl_fac1) X(rcl_fac2) X(rcl_const5r) X(rcl_const6r) X(rcl_fzrab)
+  X(rcl_const3r) X(rcl_const4r) X(rcl_fac1) X(rcl_fac2) X(rcl_const5r) X(rcl_const6r) X(rcl_fzrab) \
+  X(rnice)
 
 /*
  * Literals of cloudsc_c.c whose binary64 pattern has a non-zero low word.  FP64 instructions can
@@ -36,7 +37,7 @@
   X(zepsec, 1.0e-14) X(one_m_1em6, 1.0 - 1.0e-6) X(p0666, 0.666) X(p1296, 12.96) X(p0639, 0.639) \
   X(p0024, 0.024) X(p221, 2.21) X(p78, 7.8) X(p887, 8.87) X(p08, 0.8) X(p02, 0.2) X(p099, 0.99) \
   X(p001, 0.01) X(p03, 0.3) X(p04, 0.4) X(p05777, 0.5777) X(p078, 0.78) X(ztw1, 1329.31) \
-  X(ztw2, 0.0074615) X(ztw4, 40.637)
+  X(ztw2, 0.0074615) X(ztw4, 40.637) X(p0002, 0.002) X(p0333, 0.333)
 
 template <typename T>
 struct CloudscConst {
@@ -54,6 +55,8 @@ struct CloudscConst {
   T r_rd, r_rv, r_rtaumel, r_rlcritsnow, r_rdepliqrefdepth, r_rvrfactor, r_15000, r_273, r_p02, r_p0024;
   int nssopt;
   int ncldtop;
+  /* aerosol switches the AER instantiation of the column code honours (cloudsc_c.c:1561,1625) */
+  int laericesed, laericeauto;
 };
 
 /*

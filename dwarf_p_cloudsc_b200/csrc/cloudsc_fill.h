@@ -15,12 +15,11 @@ namespace cloudsc {
 
 /* Returns NULL if supported, else a static message naming the offending member. */
 static inline const char *check_params(const struct TECLDP *p) {
-  /* branches the reference only takes when these flags are set read extra fields and, for
-     laericesed, leak a per-column value across columns (cloudsc_c.c:1561-1566) */
-  if (p->laerliqautolsp) return "yrecldp->laerliqautolsp != 0 is not supported";
-  if (p->laerliqcoll) return "yrecldp->laerliqcoll != 0 is not supported";
-  if (p->laericesed) return "yrecldp->laericesed != 0 is not supported";
-  if (p->laericeauto) return "yrecldp->laericeauto != 0 is not supported";
+  /* laerliqautolsp / laerliqcoll only act inside the iwarmrain == 1 branch (cloudsc_c.c:1654,1679), which the
+     reference hard-codes away (:367); the two live aerosol switches laericesed (:1561) and laericeauto (:1625) are
+     implemented by the AER instantiation of the column code */
+  if (p->laerliqautolsp) return "yrecldp->laerliqautolsp != 0 is not supported (iwarmrain == 1 only)";
+  if (p->laerliqcoll) return "yrecldp->laerliqcoll != 0 is not supported (iwarmrain == 1 only)";
   if (p->nssopt < 0 || p->nssopt > 3) return "yrecldp->nssopt must be 0..3 (zqe is undefined otherwise, cloudsc_c.c:1275-1302)";
   if (p->ncldtop < 2) return "yrecldp->ncldtop must be >= 2 (level ncldtop reads level ncldtop-1, cloudsc_c.c:1390,1597,1868)";
   /* llfall pattern the unrolled species code assumes: rain and snow fall, liquid does not;
@@ -56,7 +55,12 @@ static inline void fill_consts(const struct TECLDP *p, const struct cloudsc_cons
   out->kk_num_pow_land = (T)std::pow(p->rcl_kk_cloud_num_land, p->rcl_kkbaun);
   out->nssopt = p->nssopt;
   out->ncldtop = p->ncldtop;
+  out->laericesed = p->laericesed ? 1 : 0;
+  out->laericeauto = p->laericeauto ? 1 : 0;
 }
+
+/* bit 0: PRE_ICE is read (laericesed), bit 1: PICRIT_AER and PNICE are read (laericeauto) */
+static inline int aerosol_mask(const struct TECLDP *p) { return (p->laericesed ? 1 : 0) | (p->laericeauto ? 2 : 0); }
 
 /* Per-launch constants; every member is computed in T with the reference's own expression. */
 template <typename T>

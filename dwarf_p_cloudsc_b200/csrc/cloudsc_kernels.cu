@@ -11,6 +11,7 @@
 #include "cloudsc_column.cuh"
 #include "cloudsc_fill.h"
 
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 
@@ -77,6 +78,11 @@ struct GlobalIO {
     return __ldg(base + off);
   }
   template <int S> __device__ __forceinline__ T ld_next(int k) const { return ld<S>(k + 1); }
+  /* aerosol inputs ([klev] fields), only read by the AER instantiation where the matching flag is set */
+  template <int A> __device__ __forceinline__ T ld_aer(int k) const {
+    const T *base = static_cast<const T *>(ft.p[A == AER_RE_ICE ? CLOUDSC_F_PRE_ICE : A == AER_ICRIT ? CLOUDSC_F_PICRIT_AER : CLOUDSC_F_PNICE]);
+    return __ldg(base + offL + (long long)k * stride);
+  }
   __device__ __forceinline__ T paph_row(int r) const { return ld<IN_PAPH>(r); }
   template <int S> __device__ __forceinline__ void st(int k, T v) {
     T *base = static_cast<T *>(ft.p[out_field(S)]);
@@ -92,7 +98,7 @@ struct GlobalIO {
   __device__ __forceinline__ void level_end(int) {}
 };
 
-template <typename T, int BLOCK, int MINB>
+template <typename T, int BLOCK, int MINB, bool AER>
 __global__ void __launch_bounds__(BLOCK, MINB)
 cloudsc_sweep_direct(const __grid_constant__ FieldTable ft, const LaunchGeom g, const __grid_constant__ StepConst<T> sc) {
   const int col = g.col_begin + blockIdx.x * BLOCK + threadIdx.x;
@@ -105,7 +111,7 @@ cloudsc_sweep_direct(const __grid_constant__ FieldTable ft, const LaunchGeom g, 
                  (long long)ibl * 5 * g.klev * g.nproma + jl,
                  (long long)ibl * g.nproma + jl,
                  g.nproma, g.klev};
-  cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+  cloudsc_column<T, AER>(dev_consts<T>(), sc, io, g.klev);
 }
 
 /* ---- IO policy 2: TMA-staged input tiles shared by the CTA, streaming stores ------------------- */
@@ -579,6 +585,12 @@ cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<fl
   return cudaSuccess;
 }
 
+/* launches per kernel family since the library was loaded (cloudsc_b200_launch_counts) */
+static std::atomic<long long> g_launches[KERNEL_FAMILIES];
+void launch_counts(long long out[KERNEL_FAMILIES]) {
+  for (int i = 0; i < KERNEL_FAMILIES; ++i) out[i] = g_launches[i].load();
+}
+
 namespace {
 constexpr int kDirectBlock = 128;
 
@@ -587,8 +599,8 @@ constexpr int kDirectBlock = 128;
    and still need 3 waves for 163 840 columns (profiles/README.md); those builds were measured and dropped. */
 
 
-template <typename T, int MINB>
-cudaError_t launch_direct_mb(const FieldTable &ft, const LaunchGeom &g, double ptsphy, cudaStream_t stream) {
+template <typename T, bool AER>
+cudaError_t launch_direct(const FieldTable &ft, const LaunchGeom &g, double ptsphy, cudaStream_t stream) {
   const int ncols = g.col_end - g.col_begin;
   const int grid = (ncols + kDirectBlock - 1) / kDirectBlock;
   int dev = 0;
@@ -596,26 +608,20 @@ cudaError_t launch_direct_mb(const FieldTable &ft, const LaunchGeom &g, double p
   if (e != cudaSuccess) return e;
   StepConst<T> sc;
   fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
-  cloudsc_sweep_direct<T, kDirectBlock, MINB><<<grid, kDirectBlock, 0, stream>>>(ft, g, sc);
+  cloudsc_sweep_direct<T, kDirectBlock, 3, AER><<<grid, kDirectBlock, 0, stream>>>(ft, g, sc);
+  ++g_launches[AER ? KERNEL_DIRECT_AER : KERNEL_DIRECT];
   return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t launch_direct(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int variant, cudaStream_t stream) {
-  (void)variant;
-  return launch_direct_mb<T, 3>(ft, g, ptsphy, stream);
-}
-
-template <typename T>
-const void *direct_fn(int variant) {
-  (void)variant;
-  return (const void *)cloudsc_sweep_direct<T, kDirectBlock, 3>;
+const void *direct_fn(bool aer) {
+  return aer ? (const void *)cloudsc_sweep_direct<T, kDirectBlock, 3, true> : (const void *)cloudsc_sweep_direct<T, kDirectBlock, 3, false>;
 }
 
 /* ---- tile (TMA-staged) variant ------------------------------------------------------------------ */
 /* (warps per CTA, resident warps per SM the register budget is sized for: 8 -> 255 regs, 12 -> 168, 16 -> 128) */
 struct TileCfg { int warps, wps; };
-inline bool is_tile(int variant) { return variant == VARIANT_AUTO || (variant >= VARIANT_TILE_C4_W8 && variant <= VARIANT_TILE_C2_W12); }
+inline bool is_tile(int variant) { return variant == VARIANT_AUTO || variant == VARIANT_TILE_C4_W12 || variant == VARIANT_TILE_C1_W12 || variant == VARIANT_TILE_C2_W12; }
 /* widest CTA tile whose 32*WARPS columns never straddle an NPROMA block */
 inline int tile_warps_for(int nproma) { return nproma % 128 == 0 ? 4 : nproma % 64 == 0 ? 2 : nproma % 32 == 0 ? 1 : 0; }
 inline TileCfg tile_cfg(int variant, int nproma) {
@@ -624,9 +630,7 @@ inline TileCfg tile_cfg(int variant, int nproma) {
      -- the fastest configuration measured on B200 (profiles/README.md) */
   TileCfg c = {widest ? 1 : 0, 12};
   switch (variant) {
-    case VARIANT_TILE_C4_W8:
-    case VARIANT_TILE_C4_W12:
-    case VARIANT_TILE_C4_W16: c.warps = widest; break;
+    case VARIANT_TILE_C4_W12: c.warps = widest; break;
     case VARIANT_TILE_C2_W12: c.warps = widest >= 2 ? 2 : widest; break;
     default: break;
   }
@@ -675,13 +679,13 @@ cudaError_t launch_tile(const FieldTable &ft, const LaunchGeom &g, double ptsphy
   StepConst<T> sc;
   fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
   void *args[] = {(void *)&ft, (void *)&g, (void *)&sc};
+  ++g_launches[KERNEL_TILE];
   return cudaLaunchKernel(fn, dim3(grid), dim3(per_cta), args, smem, stream);
 }
 
 /* ---- pipe (cp.async) variant ---------------------------------------------------------------------- */
 constexpr int kPipeBlock = 32;
-inline bool is_pipe(int variant) { return variant >= VARIANT_PIPE_W12 && variant <= VARIANT_PIPE_W16; }
-inline int pipe_wps(int variant) { return variant == VARIANT_PIPE_W8 ? 8 : variant == VARIANT_PIPE_W16 ? 16 : 12; }
+inline bool is_pipe(int variant) { return variant == VARIANT_PIPE_W12; }
 
 template <typename T>
 SlotTable make_slot_table(const FieldTable &ft, const LaunchGeom &g) {
@@ -699,17 +703,16 @@ SlotTable make_slot_table(const FieldTable &ft, const LaunchGeom &g) {
 }
 
 template <typename T>
-const void *pipe_fn(int wps) {
-  (void)wps;
+const void *pipe_fn() {
   return (const void *)cloudsc_sweep_pipe<T, kPipeBlock, 12>;
 }
 
 template <typename T>
-cudaError_t launch_pipe(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int variant, cudaStream_t stream) {
+cudaError_t launch_pipe(const FieldTable &ft, const LaunchGeom &g, double ptsphy, cudaStream_t stream) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  const void *fn = pipe_fn<T>(pipe_wps(variant));
+  const void *fn = pipe_fn<T>();
   const size_t smem = PipeIO<T, kPipeBlock>::kSmem;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -721,13 +724,20 @@ cudaError_t launch_pipe(const FieldTable &ft, const LaunchGeom &g, double ptsphy
   StepConst<T> sc;
   fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
   void *args[] = {(void *)&tab, (void *)&g, (void *)&sc};
+  ++g_launches[KERNEL_PIPE];
   return cudaLaunchKernel(fn, dim3(grid), dim3(kPipeBlock), args, smem, stream);
 }
 }  // namespace
 
 template <typename T>
 static cudaError_t launch_any(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int variant, cudaStream_t stream) {
-  if (is_pipe(variant)) return launch_pipe<T>(ft, g, ptsphy, variant, stream);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  /* aerosol switches set (laericesed / laericeauto): the AER instantiation of the column code, plain loads */
+  const CloudscConst<T> &hc = host_consts<T>(dev);
+  if (hc.laericesed || hc.laericeauto) return launch_direct<T, true>(ft, g, ptsphy, stream);
+  if (is_pipe(variant)) return launch_pipe<T>(ft, g, ptsphy, stream);
   const TileCfg cfg = tile_cfg(variant, g.nproma);
   if (is_tile(variant) && tile_ok<T>(ft, g, cfg)) {
     /* the TMA kernel moves whole rows of 32*WARPS columns; a ragged last tile reads the padding columns of the last
@@ -736,7 +746,7 @@ static cudaError_t launch_any(const FieldTable &ft, const LaunchGeom &g, double 
   }
   /* geometry the TMA path cannot take (NPROMA not a multiple of 32, unaligned column range or
      pointers): same arithmetic, plain global loads */
-  return launch_direct<T>(ft, g, ptsphy, is_tile(variant) ? VARIANT_DIRECT_R168 : variant, stream);
+  return launch_direct<T, false>(ft, g, ptsphy, stream);
 }
 
 template <typename T>
@@ -749,6 +759,7 @@ static cudaError_t launch_sweep_tmap_t(const FieldTable &ft, const TensorMaps &t
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  if (host_consts<T>(dev).laericesed || host_consts<T>(dev).laericeauto) return launch_any<T>(ft, g, ptsphy, VARIANT_AUTO, stream);
   const void *fn = (const void *)cloudsc_sweep_tmap<T>;
   const size_t smem = TmapIO<T>::kSmem;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -760,6 +771,7 @@ static cudaError_t launch_sweep_tmap_t(const FieldTable &ft, const TensorMaps &t
   fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
   const int grid = (g.col_end - g.col_begin + 31) / 32;
   void *args[] = {(void *)&ft, (void *)&tm, (void *)&g, (void *)&sc};
+  ++g_launches[KERNEL_TMAP];
   return cudaLaunchKernel(fn, dim3(grid), dim3(32), args, smem, stream);
 }
 
@@ -800,20 +812,23 @@ cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsph
 }
 
 cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool aer = h_const64[dev & 63].laericesed || h_const64[dev & 63].laericeauto;
   const TileCfg cfg = tile_cfg(variant, nproma);
-  const bool pipe = is_pipe(variant);
-  const bool tile = pipe || (is_tile(variant) && cfg.warps > 0);   /* "uses dynamic shared memory" */
+  const bool pipe = !aer && is_pipe(variant);
+  const bool tile = pipe || (!aer && is_tile(variant) && cfg.warps > 0);   /* "uses dynamic shared memory" */
   cudaFuncAttributes a;
   size_t dyn = 0;
   const void *fn;
   if (pipe) {
-    fn = precision == CLOUDSC_B200_FP32 ? pipe_fn<float>(pipe_wps(variant)) : pipe_fn<double>(pipe_wps(variant));
+    fn = precision == CLOUDSC_B200_FP32 ? pipe_fn<float>() : pipe_fn<double>();
     dyn = precision == CLOUDSC_B200_FP32 ? PipeIO<float, kPipeBlock>::kSmem : PipeIO<double, kPipeBlock>::kSmem;
   } else {
-    fn = precision == CLOUDSC_B200_FP32 ? (tile ? tile_fn<float>(cfg, &dyn) : direct_fn<float>(variant))
-                                        : (tile ? tile_fn<double>(cfg, &dyn) : direct_fn<double>(variant));
+    fn = precision == CLOUDSC_B200_FP32 ? (tile ? tile_fn<float>(cfg, &dyn) : direct_fn<float>(aer))
+                                        : (tile ? tile_fn<double>(cfg, &dyn) : direct_fn<double>(aer));
   }
-  cudaError_t e;
   if (tile) {
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
@@ -835,6 +850,18 @@ cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]
   out[6] = variant;
   out[7] = (int)dyn;
   return cudaSuccess;
+}
+
+/* host mirror of the parameters set_params() uploaded to the current device */
+int sweep_ncldtop() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  return h_const64[dev & 63].ncldtop;
+}
+int sweep_aerosol_mask() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  return (h_const64[dev & 63].laericesed ? 1 : 0) | (h_const64[dev & 63].laericeauto ? 2 : 0);
 }
 
 }  // namespace cloudsc

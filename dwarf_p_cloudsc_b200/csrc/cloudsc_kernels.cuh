@@ -25,27 +25,25 @@ struct LaunchGeom {
   int klev;
 };
 
+/* (the ids are stable across rounds: 1, 3, 4, 6, 10, 11 were aliases of 2, 5, 9 and have been removed) */
 enum Variant {
   VARIANT_AUTO = 0,         /* = VARIANT_TILE_C1_W12 where NPROMA allows, else the direct kernel */
-  /* one thread per column, loads/stores straight from/to global memory (any geometry) */
-  VARIANT_DIRECT_R255 = 1,  /* (1 and 3: former 255-/128-register builds, now aliases of 2) */
+  /* one thread per column, loads/stores straight from/to global memory (any geometry; also the kernel of the
+     aerosol parameter sets, laericesed / laericeauto) */
   VARIANT_DIRECT_R168 = 2,
-  VARIANT_DIRECT_R128 = 3,
   /* TMA-staged input tiles (cp.async.bulk + mbarrier) of 32*WARPS columns per CTA, streaming stores.
-     Cn = warps per CTA (clamped to what NPROMA allows); all at 168 registers = 12 resident warps per SM
-     (4 and 6: former 255-/128-register builds, now aliases of 5) */
-  VARIANT_TILE_C4_W8 = 4,
+     Cn = warps per CTA (clamped to what NPROMA allows); all at 168 registers = 12 resident warps per SM */
   VARIANT_TILE_C4_W12 = 5,
-  VARIANT_TILE_C4_W16 = 6,
   VARIANT_TILE_C1_W12 = 7,  /* one-warp CTAs, warp-private tiles */
   VARIANT_TILE_C2_W12 = 8,
-  /* thread-private cp.async ring (LDGSTS), pre-offset slot pointers, streaming stores; any geometry
-     (10 and 11: aliases of 9) */
+  /* thread-private cp.async ring (LDGSTS), pre-offset slot pointers, streaming stores; any geometry */
   VARIANT_PIPE_W12 = 9,
-  VARIANT_PIPE_W8 = 10,
-  VARIANT_PIPE_W16 = 11,
   VARIANT_COUNT
 };
+inline bool variant_valid(int v) {
+  return v == VARIANT_AUTO || v == VARIANT_DIRECT_R168 || v == VARIANT_TILE_C4_W12 || v == VARIANT_TILE_C1_W12 ||
+         v == VARIANT_TILE_C2_W12 || v == VARIANT_PIPE_W12;
+}
 
 /*
  * Tensor maps of an ARENA-allocated input set (cloudsc_b200_create): fields of one kind lie at a
@@ -71,6 +69,12 @@ cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<fl
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,
                          cudaStream_t stream);
 cudaError_t sweep_kernel_info(int nproma, int precision, int variant, int out[8]);
+/* kernel families, for the launch counters */
+enum KernelFamily { KERNEL_TMAP, KERNEL_TILE, KERNEL_DIRECT, KERNEL_PIPE, KERNEL_DIRECT_AER, KERNEL_FAMILIES };
+void launch_counts(long long out[KERNEL_FAMILIES]);
+/* host mirrors of what set_params() uploaded to the current device: ncldtop; bit 0 = laericesed, bit 1 = laericeauto */
+int sweep_ncldtop();
+int sweep_aerosol_mask();
 
 }  // namespace cloudsc
 #endif

@@ -68,14 +68,19 @@ def expand(src: np.ndarray, ngptot: int, nproma: int, first_column: int = 0) -> 
     return np.ascontiguousarray(np.moveaxis(out, -2, 0))   # [nb, ..., nproma]
 
 
+AEROSOL_FIELDS = ("PRE_ICE", "PICRIT_AER", "PNICE")   # read with yrecldp.laericesed / laericeauto
+
+
 def blocked_fields(cols: Dict[str, np.ndarray], ngptot: int, nproma: int, klev: int,
-                   first_column: int = 0, dtype=np.float64, live_only: bool = True) -> Dict[str, np.ndarray]:
+                   first_column: int = 0, dtype=np.float64, live_only: bool = True,
+                   aerosol: bool = False) -> Dict[str, np.ndarray]:
     """Fields in driver layout: inputs expanded, outputs zero-initialised.  With ``live_only`` the
-    13 fields the kernel never touches (use N / A in the field table) are left out (NULL pointers)."""
+    13 fields the kernel never touches (use N / A in the field table) are left out (NULL pointers);
+    ``aerosol`` keeps the three aerosol inputs the laericesed / laericeauto branches read."""
     nb = nblocks_of(ngptot, nproma)
     out = {}
     for f in FIELDS:
-        if live_only and f.use in "NA":
+        if live_only and f.use in "NA" and not (aerosol and f.name in AEROSOL_FIELDS):
             continue
         shape = (nb,) + f.level_shape(klev) + (nproma,)
         if f.name in cols:
@@ -157,7 +162,12 @@ def perturb(cols: Dict[str, np.ndarray], variant: str, seed: int = 1234) -> Dict
         c["PLU"] = np.where(clear & lone, 1.0e-4, c["PLU"])
         lone = rng.random(shape) < 0.01                                       # and lone moist points that open the new-cloud window
         c["PQ"] = np.where(clear & lone & (lev > 0.5), c["PQ"] * 4.0, c["PQ"])
-    unknown = parts - {"warm", "hot", "land", "conv", "rain", "moist", "tend", "sparse", ""}
+    if "aer" in parts:         # aerosol inputs of the laericesed / laericeauto branches (identically zero in the data set)
+        shape = c["PT"].shape
+        c["PRE_ICE"] = 20.0 + 80.0 * rng.random(shape)                        # ice effective radius [um] -> fall speed 0.04..0.2
+        c["PNICE"] = 0.027 * (0.2 + 3.0 * rng.random(shape))                  # around yrecldp.rnice
+        c["PICRIT_AER"] = 3.0e-5 * (0.3 + 2.0 * rng.random(shape))            # around yrecldp.rlcritsnow
+    unknown = parts - {"warm", "hot", "land", "conv", "rain", "moist", "tend", "sparse", "aer", ""}
     if unknown:
         raise ValueError(f"unknown perturbation {unknown}")
     return c

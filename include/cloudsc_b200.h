@@ -45,7 +45,9 @@ extern "C" {
 /* kind:  L = [klev][nproma], H = [klev+1][nproma], C = [nclv][klev][nproma], S = [nproma] double,
  *        I = [nproma] int
  * use:   R read, W written, B both (in/out), N never touched by the kernel,
- *        A read only when the matching yrecldp->laer* flag is set (unsupported -> EPARAMS) */
+ *        A read only when the matching yrecldp->laer* flag is set: PRE_ICE with laericesed (cloudsc_c.c:1561-1566),
+ *          PICRIT_AER and PNICE with laericeauto (:1625-1632); PLCRIT_AER / PCCN belong to laerliqautolsp / laerliqcoll,
+ *          which only act in the iwarmrain == 1 branch the reference compiles dead (:367,1654,1679) -> EPARAMS */
 #define CLOUDSC_FIELDS(X) \
   X(PT, L, R) X(PQ, L, R) \
   X(TENDENCY_CML_T, L, N) X(TENDENCY_CML_Q, L, N) X(TENDENCY_CML_A, L, N) X(TENDENCY_CML_CLD, C, N) \
@@ -123,6 +125,10 @@ int cloudsc_b200_get_variant(void);
 /* registers/thread, spill bytes, static smem, max threads/block, achieved blocks/SM of the
  * kernel the next launch(nproma, precision) would use; out[8] ints */
 int cloudsc_b200_kernel_info(int nproma, int precision, int out[8]);
+/* number of kernels this process has launched since the library was loaded, per kernel family:
+ * out[0] tensor-map TMA kernel, [1] bulk-copy TMA kernel, [2] plain-load kernel, [3] cp.async-ring kernel,
+ * [4] plain-load kernel with the aerosol inputs (laericesed / laericeauto) */
+int cloudsc_b200_launch_counts(long long out[5]);
 
 /* ---- host-resident, end-to-end ---------------------------------------------------------- */
 /*
@@ -133,6 +139,16 @@ int cloudsc_b200_kernel_info(int nproma, int precision, int out[8]);
  */
 int cloudsc_b200_run_host(void *const host_fields[CLOUDSC_NFIELDS], int ngptot, int nproma, int klev,
                           double ptsphy, int chunk_blocks, int nstreams, double stats[4]);
+/* the same with the precision of the host arrays AND of the device arithmetic: CLOUDSC_B200_FP64 (= run_host) or
+ * CLOUDSC_B200_FP32 (float host fields, KTYPE int).
+ * What travels: of every R/B field only the rows the kernel reads (species 0..3 of PCLV / TENDENCY_TMP_CLD; no rows
+ * above level ncldtop-1 of PQ, TENDENCY_TMP_Q, PSUPSAT, PSNDE, PHRSW, PHRLW, PVERVEL, PMFU, PMFD, PAP, PLU), of every
+ * W/B field the rows it writes (species 0..3 of TENDENCY_LOC_CLD; species 4 is zeroed on the host, cloudsc_driver.c:200).
+ * Of a ragged last block only the first ngptot - (nblocks-1)*nproma columns are written back; the padding columns of
+ * the caller's output arrays stay untouched, except those of PCOVPTOT / TENDENCY_LOC_CLD, which get the zeros the
+ * reference driver writes (cloudsc_driver.c:199-200). */
+int cloudsc_b200_run_host_ex(void *const host_fields[CLOUDSC_NFIELDS], int ngptot, int nproma, int klev,
+                             double ptsphy, int precision, int chunk_blocks, int nstreams, double stats[4]);
 /* run_host keeps its streams and device staging arenas between calls (allocation costs more than
  * the copies); this frees them on every device */
 int cloudsc_b200_release_cache(void);
@@ -162,6 +178,10 @@ void *cloudsc_b200_field_ptr(cloudsc_b200_state *st, int f);
 int cloudsc_b200_sync(void *stream);
 
 /* ---- binary-compatible drop-in for the reference kernel (host pointers, one block) -------- */
+/* Re-entrant: called concurrently from the OpenMP threads of cloudsc_driver.c:191-217, each thread stages its block
+ * through thread-local device buffers on its own stream.  The buffers are freed when the thread exits, or by
+ * cloudsc_b200_release_thread() from that thread. */
+int cloudsc_b200_release_thread(void);
 int cloudsc_c(int kidia, int kfdia, int klon, int klev, double ptsphy,
   double *v_pt, double *v_pq,
   double *v_tendency_cml_t, double *v_tendency_cml_q, double *v_tendency_cml_a, double *v_tendency_cml_cld,

@@ -11,8 +11,9 @@
  * deliberately NOT the k-cached, sparse-solve organisation of the CUDA kernel, so that the two are
  * independent implementations of the same arithmetic.  Each section cites the reference lines it
  * follows.  Dead code of the reference (ztrpaus :697-712, the first sink-sum pass :2207-2227, the
- * switched-off process variants iwarmrain=1 / ievaprain=1 / ievapsnow=2 / idepice=2, the laer*
- * branches) is not restated; oracle_check_params() below states the parameter domain.
+ * switched-off process variants iwarmrain=1 / ievaprain=1 / ievapsnow=2 / idepice=2 and, with them, the
+ * laerliqautolsp / laerliqcoll branches that only exist inside iwarmrain=1) is not restated; the two live aerosol
+ * switches laericesed (:1561-1566) and laericeauto (:1625-1632) are; oracle_check_params() below states the parameter domain.
  *
  * PARITY PINNING: checked by tests/test_cpu_oracle.py against (a) the golden vectors of the
  * reference's own data set, tests/golden/reference.h5 (21 fields x 100 columns, produced by the
@@ -46,14 +47,14 @@ static double f_foeldcpm(double t) { return f_foealfa(t) * ralvdcp + (1.0 - f_fo
 int oracle_check_params(void) {
   const struct TECLDP *y = yrecldp;
   if (!y) return 0;
-  if (y->laerliqautolsp || y->laerliqcoll || y->laericesed || y->laericeauto) return 0;
+  if (y->laerliqautolsp || y->laerliqcoll) return 0;
   if (y->nssopt < 0 || y->nssopt > 3 || y->ncldtop < 2) return 0;
   return 1;
 }
 
 struct colptr {            /* one column of every field: base pointer + level stride (= klon) */
   const double *pt, *pq, *tt, *tq, *ta, *tcld, *pvfl, *pvfi, *phrsw, *phrlw, *pvervel, *pap, *paph,
-      *plu, *psnde, *pmfu, *pmfd, *pa, *pclv, *psupsat;
+      *plu, *psnde, *pmfu, *pmfd, *pa, *pclv, *psupsat, *pre_ice, *picrit_aer, *pnice;
   double plsm;
   int ktype;
   double *plude, *lt, *lq, *la, *lcld, *pcovptot, *prainfrac;
@@ -421,7 +422,11 @@ static void column(const struct colptr *c, const int klev, const double ptsphy) 
           zqxfg[m] += zfallsrce[m];
           zqpretot += zqxfg[m];
         }
-        const double zfall = zvqx[m] * zrho;
+        /* aerosol override of the ice fall speed, :1561-1566 (the reference stores it in the shared zvqx[1] and reads
+           it back on the next line for the same column; nothing else reads zvqx during the sweep) */
+        double zv = zvqx[m];
+        if (y->laericesed && m == QI) zv = 0.002 * pow(AT(c->pre_ice, k), 1.0);
+        const double zfall = zv * zrho;
         zfallsink[m] = zdtgdp * zfall;
       }
     /* precipitation cover, :1594-1611 */
@@ -439,8 +444,12 @@ static void column(const struct colptr *c, const int klev, const double ptsphy) 
 
     /* 4.3a autoconversion to snow, :1616-1637 */
     if (t <= rtt && zicecld > zepsec) {
-      const double zzco = (ptsphy * y->rsnowlin1) * exp(y->rsnowlin2 * (t - rtt));
-      const double zlcrit = y->rlcritsnow;
+      double zzco = (ptsphy * y->rsnowlin1) * exp(y->rsnowlin2 * (t - rtt));
+      double zlcrit = y->rlcritsnow;
+      if (y->laericeauto) {                     /* :1625-1632 */
+        zlcrit = AT(c->picrit_aer, k);
+        zzco = zzco * pow(y->rnice / AT(c->pnice, k), 0.333);
+      }
       zsnowaut = zzco * (1.0 - exp(-sq2(zicecld / zlcrit)));
       zsolqb[QI][QS] += zsnowaut;
     }
@@ -719,7 +728,7 @@ int cloudsc_oracle(int kidia, int kfdia, int klon, int klev, double ptsphy,
   double *v_pfplsl, double *v_pfplsn, double *v_pfhpsl, double *v_pfhpsn) {
   (void)v_tendency_cml_t; (void)v_tendency_cml_q; (void)v_tendency_cml_a; (void)v_tendency_cml_cld;
   (void)v_pvfa; (void)v_pdyna; (void)v_pdynl; (void)v_pdyni;
-  (void)v_plcrit_aer; (void)v_picrit_aer; (void)v_pre_ice; (void)v_pccn; (void)v_pnice;
+  (void)v_plcrit_aer; (void)v_pccn;
   if (!oracle_check_params() || klev > MAXLEV || klev < 2) return -1;
   for (int jl = kidia - 1; jl < kfdia; jl++) {
     struct colptr c;
@@ -729,6 +738,8 @@ int cloudsc_oracle(int kidia, int kfdia, int klon, int klev, double ptsphy,
     c.phrsw = v_phrsw + jl; c.phrlw = v_phrlw + jl; c.pvervel = v_pvervel + jl; c.pap = v_pap + jl;
     c.paph = v_paph + jl; c.plu = v_plu + jl; c.psnde = v_psnde + jl; c.pmfu = v_pmfu + jl; c.pmfd = v_pmfd + jl;
     c.pa = v_pa + jl; c.pclv = v_pclv + jl; c.psupsat = v_psupsat + jl;
+    c.pre_ice = v_pre_ice ? v_pre_ice + jl : NULL; c.picrit_aer = v_picrit_aer ? v_picrit_aer + jl : NULL;
+    c.pnice = v_pnice ? v_pnice + jl : NULL;
     c.plsm = v_plsm[jl]; c.ktype = v_ktype[jl];
     c.plude = v_plude + jl; c.lt = v_tendency_loc_t + jl; c.lq = v_tendency_loc_q + jl; c.la = v_tendency_loc_a + jl;
     c.lcld = v_tendency_loc_cld + jl; c.pcovptot = v_pcovptot + jl; c.prainfrac = v_prainfrac_toprfz + jl;

@@ -44,6 +44,10 @@ struct HostIO {
     return ((const T *)f[in_field(S)])[(size_t)(sp * klev + k) * stride + jl];
   }
   template <int S> T ld_next(int k) const { return ld<S>(k + 1); }
+  template <int A> T ld_aer(int k) const {
+    const int fi = A == AER_RE_ICE ? CLOUDSC_F_PRE_ICE : A == AER_ICRIT ? CLOUDSC_F_PICRIT_AER : CLOUDSC_F_PNICE;
+    return ((const T *)f[fi])[(size_t)k * stride + jl];
+  }
   T paph_row(int r) const { return ld<IN_PAPH>(r); }
   template <int S> void st(int k, T v) {
     const int sp = (S >= OUT_TCLD0 && S <= OUT_TCLD4) ? S - OUT_TCLD0 : 0;
@@ -90,6 +94,9 @@ int run(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fiel
         io.f = pb; io.jl = jl; io.stride = nproma; io.klev = klev;
         for (int i = 0; i < PARK_COUNT; i++) io.slots[i] = T(-1.0e300);   /* poison: every slot must be written first */
         cloudsc_column<T>(c, sc, io, klev);
+      } else if (aerosol_mask(p)) {   /* the instantiation the device launches when laericesed / laericeauto are set */
+        HostIO<T> io{pb, jl, nproma, klev};
+        cloudsc_column<T, true>(c, sc, io, klev);
       } else {
         HostIO<T> io{pb, jl, nproma, klev};
         cloudsc_column<T>(c, sc, io, klev);

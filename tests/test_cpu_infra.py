@@ -106,7 +106,7 @@ def test_abi_library_exports_every_declared_symbol(built):
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(cloudsc_b200_\w+|cloudsc_c)\s*\(", hdr))
     declared.discard("cloudsc_b200_state")
-    assert len(declared) == 30, sorted(declared)
+    assert len(declared) >= 33 and {"cloudsc_b200_run_host_ex", "cloudsc_b200_release_thread", "cloudsc_b200_launch_counts"} <= declared, sorted(declared)
     lib = ctypes.CDLL(os.path.join(ROOT, "dwarf_p_cloudsc_b200", "lib", "libcloudsc_b200.so"))
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/cloudsc_b200.h but not exported"

@@ -230,3 +230,63 @@ def test_oracle_is_not_interposed_by_the_product_library(built, input_data):
         orc.run(F, p, k, 100, 32, klev, scalars["PTSPHY"], 2)
         got = state.unblock(F["PFPLSN"], 100)
         assert np.abs(got - ref["PFPLSN"]).max() <= 1e-12 * np.abs(ref["PFPLSN"]).max()
+
+
+AEROSOL_CASES = [(1, 0), (0, 1), (1, 1)]
+
+
+@pytest.mark.parametrize("sed,auto", AEROSOL_CASES)
+@pytest.mark.parametrize("variant", ["aer", "aer+warm+land+conv+rain+moist+tend", "aer+sparse"])
+def test_aerosol_switches_are_bit_identical_on_the_cpu(built, input_data, sed, auto, variant):
+    """yrecldp->laericesed (cloudsc_c.c:1561-1566, reads pre_ice) and laericeauto (:1625-1632, reads picrit_aer,
+    pnice) are runtime switches of the reference kernel.  The unmodified reference build, the plain-C port and the
+    strict host build of the device column code (its AER instantiation) agree bit for bit; the switches change the
+    answer; the fast arithmetic mode stays inside the FP64 tolerance."""
+    import pyemul
+    import pyoracle
+    from dwarf_p_cloudsc_b200 import params, state, validate
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    c2 = state.perturb(cols, variant)
+    ngptot, nproma = 100, 16
+    A = state.blocked_fields(c2, ngptot, nproma, klev, aerosol=True)
+    base = {n: a.copy() for n, a in A.items()}
+    orc = pyoracle.best_oracle()
+    orc.run(base, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)          # switches off
+    p.laericesed, p.laericeauto = sed, auto
+    runs = {}
+    for how in ("best", "port", "emul", "fast"):
+        B = {n: a.copy() for n, a in A.items()}
+        if how == "best":
+            orc.run(B, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+        elif how == "port":
+            pyoracle.PortOracle().run(B, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+        else:
+            pyemul.Emul(fast=(how == "fast")).run(B, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
+        runs[how] = B
+    changed = False
+    for f in params.OUTPUT_FIELDS:
+        ref = state.unblock(runs["best"][f.name], ngptot)
+        assert np.isfinite(ref).all(), f.name
+        changed |= not np.array_equal(ref, state.unblock(base[f.name], ngptot))
+        for how in ("port", "emul"):
+            got = state.unblock(runs[how][f.name], ngptot)
+            assert np.array_equal(ref, got), (how, f.name, float(np.abs(ref - got).max()))
+    assert changed, "the aerosol switches had no effect on this input set"
+    errs = validate.validate(runs["fast"], runs["best"], ngptot)
+    assert validate.all_pass(errs), "\n" + validate.format_table(errs)
+
+
+def test_warm_rain_only_aerosol_switches_are_refused(built, input_data):
+    """laerliqautolsp / laerliqcoll only act inside the iwarmrain == 1 branch the reference hard-codes away
+    (cloudsc_c.c:367,1654,1679); the port and the device column code refuse them instead of silently ignoring them."""
+    import pyemul
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    F = state.blocked_fields(cols, 32, 32, klev)
+    for name in ("laerliqautolsp", "laerliqcoll"):
+        setattr(p, name, 1)
+        with pytest.raises(RuntimeError):
+            pyemul.Emul().run(F, p, k, 32, 32, klev, scalars["PTSPHY"])
+        setattr(p, name, 0)
