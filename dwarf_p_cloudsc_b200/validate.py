@@ -79,6 +79,66 @@ def field_error(name: str, got: np.ndarray, ref: np.ndarray, ngptot: int) -> Fie
                       float(np.abs(ref).max()), errsum / ngptot, 100.0 * rel, iopt, rel_l1, rel > 10.0 * EPS)
 
 
+def _merge(name: str, parts, ngptot: int) -> FieldError:
+    """Combine partial sums (min, max, maxerr, errsum, refsum_true, refsum_c, refmax) into one FieldError."""
+    mn = min(p[0] for p in parts); mx = max(p[1] for p in parts); maxerr = max(p[2] for p in parts)
+    errsum = float(sum(p[3] for p in parts)); refsum_true = float(sum(p[4] for p in parts))
+    refsum_c = float(sum(p[5] for p in parts)); refmax = max(p[6] for p in parts)
+    if errsum < EPS:
+        rel, iopt = 0.0, 1
+    elif refsum_c < EPS:
+        rel, iopt = errsum / (1.0 + refsum_c), 2
+    else:
+        rel, iopt = errsum / refsum_c, 3
+    rel_l1 = 0.0 if errsum == 0.0 else (errsum / refsum_true if refsum_true > 0 else float("inf"))
+    return FieldError(name, float(mn), float(mx), float(maxerr), errsum, refsum_true, refsum_c, float(refmax),
+                      errsum / ngptot, 100.0 * rel, iopt, rel_l1, rel > 10.0 * EPS)
+
+
+def _partial(got: np.ndarray, ref: np.ndarray):
+    diff = np.abs(got - ref)
+    aref = np.abs(ref)
+    # sums over a broadcast reference count every replica: broadcast explicitly where shapes differ
+    if aref.shape != diff.shape:
+        reps = diff.size // aref.size
+        return (got.min(), got.max(), diff.max(), diff.sum(dtype=np.float64), aref.sum(dtype=np.float64) * reps,
+                np.trunc(aref).sum(dtype=np.float64) * reps, aref.max())
+    return (got.min(), got.max(), diff.max(), diff.sum(dtype=np.float64), aref.sum(dtype=np.float64),
+            np.trunc(aref).sum(dtype=np.float64), aref.max())
+
+
+def validate_replicated(fields: Dict[str, np.ndarray], reference_columns: Dict[str, np.ndarray], ngptot: int, nproma: int,
+                        first_column: int = 0) -> List[FieldError]:
+    """The dwarf's check at full size: EVERY column of blocked output arrays [nb, ..., nproma] against the reference
+    data set replicated the way load_reference / expand_* replicate it (global column g -> g mod nlon,
+    load_state.c:123-138,701-760; `first_column` = this rank's offset, expand_mod.F90:30-46).  The replicated reference
+    repeats every lcm(nproma, nlon) columns, so it is built for one period of blocks and broadcast -- no full-size copy."""
+    from .state import expand
+    out = []
+    nb = (ngptot + nproma - 1) // nproma
+    for name in VALIDATE_ORDER:
+        got = np.asarray(fields[name])
+        if got.dtype != np.float64:
+            got = got.astype(np.float64)
+        ref = np.asarray(reference_columns[name], dtype=np.float64)
+        nlon = ref.shape[-1]
+        period = int(np.lcm(nproma, nlon)) // nproma                   # blocks after which the pattern repeats
+        exp = expand(ref, min(nb, period) * nproma, nproma, first_column)     # [min(nb, period), ..., nproma]
+        valid_last = ngptot - (nb - 1) * nproma
+        nfullblk = nb if valid_last == nproma else nb - 1               # blocks whose columns are all valid
+        parts = []
+        whole = (nfullblk // period) * period if period <= nfullblk else 0
+        if whole:
+            g = got[:whole].reshape((whole // period, period) + got.shape[1:])
+            parts.append(_partial(g, exp[None]))
+        for b in range(whole, nfullblk):
+            parts.append(_partial(got[b], exp[b % period]))
+        if nfullblk < nb:
+            parts.append(_partial(got[nb - 1][..., :valid_last], exp[(nb - 1) % period][..., :valid_last]))
+        out.append(_merge(name, parts, ngptot))
+    return out
+
+
 def validate(fields: Dict[str, np.ndarray], reference: Dict[str, np.ndarray], ngptot: int) -> List[FieldError]:
     """fields/reference: blocked arrays [nb, ..., nproma] of the 21 validated outputs."""
     out = []

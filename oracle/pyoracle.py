@@ -71,6 +71,36 @@ class RefOracle(_Oracle):
     libname = os.path.join("_ref", "libcloudsc_ref.so")
     blocks_fn = "cloudsc_ref_blocks"
     kind = "reference"
+    flags = "-O2 -ffp-contract=off"
+
+
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+class RefFastOracle(_Oracle):
+    """The same unmodified reference kernel, built for speed (-O3, -march=x86-64-v4 where the host has AVX-512, else
+    -v3; FP contraction on).  TIMING ONLY: parity is always judged against RefOracle (-O2, contraction off)."""
+    blocks_fn = "cloudsc_ref_blocks"
+    kind = "reference"
+
+    def __init__(self):
+        flags = _cpu_flags()
+        v4 = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags
+        v3 = {"avx2", "fma", "bmi2"} <= flags
+        if not v3:
+            raise OSError("host CPU lacks AVX2/FMA: no fast reference build for it")
+        self.level = "v4" if v4 else "v3"
+        self.libname = os.path.join("_ref", f"libcloudsc_ref_O3{self.level}.so")
+        self.flags = f"-O3 -march=x86-64-{self.level} -ffp-contract=fast"
+        super().__init__()
 
 
 class PortOracle(_Oracle):
@@ -85,3 +115,49 @@ def best_oracle():
         return RefOracle()
     except (FileNotFoundError, OSError):
         return PortOracle()
+
+
+class GpuRef:
+    """The reference's OWN CUDA kernels (src/cloudsc_cuda/cloudsc/cloudsc_c_k_caching.cu / cloudsc_c.cu, unmodified,
+    compiled for sm_100a by `make -C oracle gpuref`) behind oracle/gpu_ref_harness.cu: the same-device GPU baseline.
+    ``fields`` are FP64 device arrays (torch tensors or raw pointers) in the driver layout, KLEV = 137."""
+    libs = {"kcaching": "libcloudsc_gpuref_kcaching.so", "scc": "libcloudsc_gpuref_scc.so"}
+    sources = {"kcaching": "src/cloudsc_cuda/cloudsc/cloudsc_c_k_caching.cu", "scc": "src/cloudsc_cuda/cloudsc/cloudsc_c.cu"}
+
+    def __init__(self, which="kcaching"):
+        path = os.path.join(HERE, "_ref", self.libs[which])
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.which = which
+        self.source = self.sources[which]
+        self.lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
+        self.lib.cloudsc_gpuref_run.restype = ctypes.c_int
+        self.lib.cloudsc_gpuref_run.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
+                                                ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+        self.lib.cloudsc_gpuref_kernel_info.argtypes = [ctypes.POINTER(ctypes.c_int)]
+
+    def kernel_info(self):
+        out = (ctypes.c_int * 4)()
+        rc = self.lib.cloudsc_gpuref_kernel_info(out)
+        if rc:
+            raise RuntimeError(f"cloudsc_gpuref_kernel_info: CUDA error {rc}")
+        return {"registers": out[0], "local_bytes": out[1], "static_smem": out[2], "max_threads_per_block": out[3]}
+
+    def run(self, fields, p, k, ngptot, nproma, ptsphy, plude0=None, warmup=0, reps=1):
+        """-> {"ms": mean, "ms_min": ..., "ms_max": ...} over ``reps`` launches; outputs are left in ``fields``."""
+        from dwarf_p_cloudsc_b200.params import FIELDS, KERNEL_CONSTS
+        assert ctypes.sizeof(p) == self.lib.cloudsc_gpuref_tecldp_bytes(), "struct TECLDP layout differs"
+        tab = (ctypes.c_void_p * len(FIELDS))()
+        for f in FIELDS:
+            a = fields.get(f.name)
+            if a is not None:
+                tab[f.index] = a.data_ptr() if hasattr(a, "data_ptr") else int(a)
+        kk = (ctypes.c_double * 28)(*[getattr(k, n) for n in KERNEL_CONSTS])
+        ms = (ctypes.c_float * 3)()
+        p0 = None if plude0 is None else ctypes.c_void_p(plude0.data_ptr() if hasattr(plude0, "data_ptr") else int(plude0))
+        rc = self.lib.cloudsc_gpuref_run(tab, ctypes.addressof(p), kk, int(ngptot), int(nproma), float(ptsphy), p0,
+                                         int(warmup), int(reps), ms)
+        if rc:
+            raise RuntimeError(f"cloudsc_gpuref_run: CUDA error {rc}")
+        return {"ms": ms[0], "ms_min": ms[1], "ms_max": ms[2]}

@@ -170,3 +170,20 @@ def test_c_and_python_h5lite_agree_on_random_files(hostlib, tmp_path):
         os.remove(path)
 
     check()
+
+
+def test_validate_replicated_equals_the_plain_validator():
+    """bench.py validates every column of every rank's shard against the replicated reference without building a
+    full-size copy of it (validate.validate_replicated); same numbers as the plain table on an explicit expansion,
+    incl. rank offsets, ragged last blocks and NGPTOT below one replication period."""
+    import numpy as np
+    from dwarf_p_cloudsc_b200 import state, validate
+    ref = state.load_reference()
+    rng = np.random.default_rng(0)
+    for ngptot, nproma, fc in ((1000, 128, 0), (7000, 64, 300), (3333, 32, 17), (250, 100, 5), (90, 16, 0)):
+        R = {n: state.expand(a, ngptot, nproma, fc) for n, a in ref.items()}
+        G = {n: a + 1e-9 * rng.standard_normal(a.shape) * np.abs(a).max() for n, a in R.items()}
+        for a, b in zip(validate.validate(G, R, ngptot), validate.validate_replicated(G, ref, ngptot, nproma, fc)):
+            assert a.name == b.name
+            for x, y in zip(a[1:], b[1:]):
+                assert x == y or abs(x - y) <= 1e-12 * max(abs(x), abs(y)), (ngptot, nproma, a.name, a, b)

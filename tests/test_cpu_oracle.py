@@ -290,3 +290,25 @@ def test_warm_rain_only_aerosol_switches_are_refused(built, input_data):
         with pytest.raises(RuntimeError):
             pyemul.Emul().run(F, p, k, 32, 32, klev, scalars["PTSPHY"])
         setattr(p, name, 0)
+
+
+def test_fast_reference_build_is_the_same_kernel(built, input_data):
+    """bench.py's CPU arm also times the unmodified reference kernel built for speed (-O3 -march=x86-64-v3/v4, FP
+    contraction on; oracle/Makefile `reffast`).  It is a timing build only, but it must still be the same computation:
+    within the FP64 tolerance of the -O2 parity build on the shipped and the busiest synthetic input set."""
+    import pyoracle
+    from dwarf_p_cloudsc_b200 import params, state, validate
+    try:
+        ref, fast = pyoracle.RefOracle(), pyoracle.RefFastOracle()
+    except (FileNotFoundError, OSError) as exc:
+        pytest.skip(f"needs oracle/_ref builds this host can run: {exc}")
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    for variant in ("", "warm+land+conv+rain+moist+tend"):
+        c2 = state.perturb(cols, variant)
+        A = state.blocked_fields(c2, 300, 32, klev)
+        B = {n: a.copy() for n, a in A.items()}
+        ref.run(A, p, k, 300, 32, klev, scalars["PTSPHY"], 2)
+        fast.run(B, p, k, 300, 32, klev, scalars["PTSPHY"], 2)
+        errs = validate.validate(B, A, 300)
+        assert validate.all_pass(errs), (variant, "\n" + validate.format_table(errs))

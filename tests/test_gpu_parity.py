@@ -669,3 +669,63 @@ def test_full_size_properties_arena_state(built, input_data):
         assert np.array_equal(u, base[..., idx]), f"{name}: replicated columns differ"
         assert validate.field_error(name, base, ref[name], 100).passes(), name
         assert np.array_equal(u, state.unblock(G2[name], ngptot)), f"{name}: the two device paths differ"
+
+
+@pytest.mark.parametrize("which", ["kcaching", "scc"])
+def test_reference_cuda_kernels_agree_with_ours(built, oracle, input_data, which):
+    """The reference's own CUDA kernels (cloudsc_c_k_caching.cu / cloudsc_c.cu, unmodified, compiled for sm_100a into
+    oracle/_ref by `make -C oracle gpuref`) launched as cloudsc_driver.cu:391-416 does: their outputs meet the FP64 bar
+    against the CPU oracle and against the product kernel on the same device fields.  This is the harness behind
+    bench.py's `gpu_reference` (the same-device number to beat)."""
+    import torch
+    import pyoracle
+    from dwarf_p_cloudsc_b200 import params, state, validate
+    try:
+        g = pyoracle.GpuRef(which)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libcloudsc_gpuref_*.so did not travel with this snapshot")
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    ngptot, nproma = 1024, 128
+    F = state.blocked_fields(cols, ngptot, nproma, klev)
+    R = {n: a.copy() for n, a in F.items()}
+    oracle.run(R, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 0)
+    ours = _run_gpu({n: a.copy() for n, a in F.items()}, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
+    D = _torch_fields(F)
+    t = g.run(D, p, k, ngptot, nproma, scalars["PTSPHY"])
+    torch.cuda.synchronize()
+    assert t["ms"] > 0
+    G = {n: x.cpu().numpy() for n, x in D.items()}
+    _compare(G, R, ngptot)
+    _compare(G, ours, ngptot)
+    info = g.kernel_info()
+    assert info["registers"] > 0
+
+
+@pytest.mark.parametrize("args", [("4", "1000", "128"), ("4", "100", "16"), ("3", "2500", "64")])
+def test_level0_link_of_the_reference_driver(built, args):
+    """INTEGRATION.md level 0: the reference's OWN dwarf_cloudsc.c + cloudsc_driver.c + cloudsc_validate.c + mycpu.c,
+    unmodified, linked against libcloudsc_b200.so (oracle/Makefile `level0`).  Its OpenMP threads call the cloudsc_c()
+    shim concurrently on disjoint blocks (cloudsc_driver.c:191-217); the table it prints is the reference's own
+    (cloudsc_validate.c:193-216).  Bar per field: AbsMaxErr <= 1e-9 * max|value| (the FP64 max-norm bar; the reference's
+    table does not carry sum|ref|), every value finite."""
+    import math
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "dwarf-cloudsc-c-level0")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dwarf-cloudsc-c-level0 did not travel with this snapshot")
+    env = dict(os.environ, OMP_NUM_THREADS=args[0], OMP_STACKSIZE="64M")
+    r = subprocess.run([exe, *args], cwd=os.path.join(root, "tests", "golden"), capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert f"NUMOMP={args[0]}, NGPTOT={args[1]}, NPROMA={args[2]}" in r.stdout, r.stdout
+    rows = [l.split() for l in r.stdout.splitlines() if len(l.split()) >= 7 and l.split()[1][:2] == "2D"]
+    assert len(rows) == 21, r.stdout
+    for row in rows:
+        name, vmin, vmax, maxerr, avgerr, relerr = row[0], *map(float, row[2:7])
+        assert all(math.isfinite(v) for v in (vmin, vmax, maxerr, avgerr, relerr)), row
+        assert maxerr <= 1e-9 * max(abs(vmin), abs(vmax)), (name, maxerr, vmin, vmax, r.stdout)
+    # per-thread rows: every OpenMP thread made calls
+    trows = [l for l in r.stdout.splitlines() if "@ core#" in l]
+    assert len(trows) == int(args[0]), r.stdout

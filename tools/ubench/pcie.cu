@@ -1,34 +1,147 @@
-// Host<->device copy bandwidth with page-locked memory: H2D alone, D2H alone, both directions at once.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pcie pcie.cu
-#include <chrono>
+// Host<->device copy bandwidth, 1..N GPUs AT THE SAME TIME: H2D alone, D2H alone, both directions at once, for three
+// kinds of page-locked host memory.  The end-to-end path of the library (cloudsc_b200_run_host) is bound by these
+// numbers; bench.py's e2e figure is reported against them (profiles/r2_pcie_concurrency.txt).
+//
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Xcompiler -pthread -o pcie pcie.cu
+//   run:   ./pcie [--gpus N] [--mb 1024] [--reps 3] [--mode hostalloc|wc|thp|all] [--chunk-mb 0] [--bind 0|1]
+//
+//   hostalloc  cudaHostAlloc(cudaHostAllocPortable)                      (what cloudsc_b200_host_alloc / torch pin_memory give)
+//   wc         the H2D source additionally cudaHostAllocWriteCombined    (uncached on the CPU side: no snoops on device reads)
+//   thp        aligned_alloc(2 MB) + madvise(MADV_HUGEPAGE) + first touch by the GPU's own host thread + cudaHostRegister
+//              (2 MB pages: 512x fewer IOMMU translations; first touch places the pages on the toucher's NUMA node)
+//   --chunk-mb k   issue every transfer as k-MB pieces (what a chunked pipeline does) instead of one copy
+//   --bind 1       pin host thread g to the g-th slice of the online CPUs before it allocates/touches its buffers
+// One host thread per GPU; every phase starts behind a barrier and is timed per GPU with CUDA events; the aggregate is
+// total bytes / slowest GPU.
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include <pthread.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <cuda_runtime.h>
-static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-int main() {
-  const size_t n = 2ull << 30;
-  char *h1, *h2, *d1, *d2;
-  cudaHostAlloc(&h1, n, cudaHostAllocPortable); cudaHostAlloc(&h2, n, cudaHostAllocPortable);
-  memset(h1, 1, n); memset(h2, 2, n);
-  cudaMalloc(&d1, n); cudaMalloc(&d2, n);
-  cudaStream_t s1, s2; cudaStreamCreate(&s1); cudaStreamCreate(&s2);
-  for (int rep = 0; rep < 2; ++rep) {
-    double t = now(); cudaMemcpyAsync(d1, h1, n, cudaMemcpyHostToDevice, s1); cudaStreamSynchronize(s1);
-    printf("H2D alone      %6.1f GB/s\n", n / (now() - t) / 1e9);
-    t = now(); cudaMemcpyAsync(h2, d2, n, cudaMemcpyDeviceToHost, s2); cudaStreamSynchronize(s2);
-    printf("D2H alone      %6.1f GB/s\n", n / (now() - t) / 1e9);
-    t = now(); cudaMemcpyAsync(d1, h1, n, cudaMemcpyHostToDevice, s1); cudaMemcpyAsync(h2, d2, n, cudaMemcpyDeviceToHost, s2);
-    cudaStreamSynchronize(s1); cudaStreamSynchronize(s2);
-    printf("H2D + D2H      %6.1f GB/s total\n", 2.0 * n / (now() - t) / 1e9);
-    // chunked: 64 copies of 8 MB each way
-    t = now();
-    for (int i = 0; i < 256; ++i) { cudaMemcpyAsync(d1 + i * (8ull << 20), h1 + i * (8ull << 20), 8ull << 20, cudaMemcpyHostToDevice, s1);
-                                    cudaMemcpyAsync(h2 + i * (8ull << 20), d2 + i * (8ull << 20), 8ull << 20, cudaMemcpyDeviceToHost, s2); }
-    cudaStreamSynchronize(s1); cudaStreamSynchronize(s2);
-    printf("H2D + D2H 8MB  %6.1f GB/s total\n", 2.0 * n / (now() - t) / 1e9);
+
+static pthread_barrier_t g_bar;
+struct Result { float h2d = 0, d2h = 0, bi_h2d = 0, bi_d2h = 0, bi_wall = 0; int ok = 0; };
+
+static void *alloc_host(const std::string &mode, size_t n, bool upload_side) {
+  void *p = nullptr;
+  if (mode == "thp") {
+    p = aligned_alloc(2u << 20, n);
+    if (!p) return nullptr;
+    madvise(p, n, MADV_HUGEPAGE);
+    memset(p, 1, n);   // first touch from this thread
+    if (cudaHostRegister(p, n, cudaHostRegisterPortable) != cudaSuccess) return nullptr;
+    return p;
   }
-  double t = now(); void *p; cudaMalloc(&p, 1 << 28); printf("cudaMalloc 256MB %.3f ms\n", (now() - t) * 1e3);
-  t = now(); cudaFree(p); printf("cudaFree %.3f ms\n", (now() - t) * 1e3);
-  t = now(); char *hp; cudaHostAlloc(&hp, 1ull << 30, cudaHostAllocPortable); printf("cudaHostAlloc 1GB %.1f ms\n", (now() - t) * 1e3);
+  unsigned flags = cudaHostAllocPortable;
+  if (mode == "wc" && upload_side) flags |= cudaHostAllocWriteCombined;
+  if (cudaHostAlloc(&p, n, flags) != cudaSuccess) return nullptr;
+  memset(p, 1, n);
+  return p;
+}
+
+static void copy(char *dst, const char *src, size_t n, size_t chunk, cudaMemcpyKind kind, cudaStream_t s) {
+  if (!chunk || chunk >= n) { cudaMemcpyAsync(dst, src, n, kind, s); return; }
+  for (size_t o = 0; o < n; o += chunk) cudaMemcpyAsync(dst + o, src + o, std::min(chunk, n - o), kind, s);
+}
+
+static void worker(int g, int ngpu, const std::string &mode, size_t n, size_t chunk, int reps, bool bind, Result *out) {
+  if (bind) {
+    const int ncpu = (int)sysconf(_SC_NPROCESSORS_ONLN), per = std::max(1, ncpu / ngpu);
+    cpu_set_t set; CPU_ZERO(&set);
+    for (int c = g * per; c < std::min(ncpu, (g + 1) * per); ++c) CPU_SET(c, &set);
+    sched_setaffinity(0, sizeof(set), &set);
+  }
+  cudaSetDevice(g);
+  char *h_up = (char *)alloc_host(mode, n, true), *h_dn = (char *)alloc_host(mode, n, false), *d_up = nullptr, *d_dn = nullptr;
+  cudaMalloc(&d_up, n); cudaMalloc(&d_dn, n);
+  cudaStream_t s1, s2; cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+  cudaEvent_t a1, b1, a2, b2; cudaEventCreate(&a1); cudaEventCreate(&b1); cudaEventCreate(&a2); cudaEventCreate(&b2);
+  const bool ok = h_up && h_dn && d_up && d_dn;
+  if (ok) { cudaMemcpy(d_up, h_up, n, cudaMemcpyHostToDevice); cudaMemcpy(h_dn, d_dn, n, cudaMemcpyDeviceToHost); }  // warm-up
+  auto gbs = [&](float ms) { return ms > 0 ? (float)((double)n * reps / (ms * 1e6)) : 0.f; };
+  float ms;
+  // --- H2D alone
+  pthread_barrier_wait(&g_bar);
+  if (ok) {
+    cudaEventRecord(a1, s1);
+    for (int r = 0; r < reps; ++r) copy(d_up, h_up, n, chunk, cudaMemcpyHostToDevice, s1);
+    cudaEventRecord(b1, s1); cudaEventSynchronize(b1); cudaEventElapsedTime(&ms, a1, b1); out->h2d = gbs(ms);
+  }
+  // --- D2H alone
+  pthread_barrier_wait(&g_bar);
+  if (ok) {
+    cudaEventRecord(a2, s2);
+    for (int r = 0; r < reps; ++r) copy(h_dn, d_dn, n, chunk, cudaMemcpyDeviceToHost, s2);
+    cudaEventRecord(b2, s2); cudaEventSynchronize(b2); cudaEventElapsedTime(&ms, a2, b2); out->d2h = gbs(ms);
+  }
+  // --- both directions
+  pthread_barrier_wait(&g_bar);
+  if (ok) {
+    cudaEventRecord(a1, s1); cudaEventRecord(a2, s2);
+    for (int r = 0; r < reps; ++r) {
+      copy(d_up, h_up, n, chunk, cudaMemcpyHostToDevice, s1);
+      copy(h_dn, d_dn, n, chunk, cudaMemcpyDeviceToHost, s2);
+    }
+    cudaEventRecord(b1, s1); cudaEventRecord(b2, s2);
+    cudaEventSynchronize(b1); cudaEventSynchronize(b2);
+    cudaEventElapsedTime(&ms, a1, b1); out->bi_h2d = gbs(ms);
+    float ms2; cudaEventElapsedTime(&ms2, a2, b2); out->bi_d2h = gbs(ms2);
+    out->bi_wall = std::max(ms, ms2);
+  }
+  pthread_barrier_wait(&g_bar);
+  out->ok = ok;
+  if (mode == "thp") { if (h_up) { cudaHostUnregister(h_up); free(h_up); } if (h_dn) { cudaHostUnregister(h_dn); free(h_dn); } }
+  else { if (h_up) cudaFreeHost(h_up); if (h_dn) cudaFreeHost(h_dn); }
+  cudaFree(d_up); cudaFree(d_dn);
+}
+
+int main(int argc, char **argv) {
+  int ngpu = 1, reps = 3, bind = 0;
+  size_t mb = 1024, chunk_mb = 0;
+  std::string mode = "all";
+  for (int i = 1; i + 1 < argc; i += 2) {
+    std::string a = argv[i];
+    if (a == "--gpus") ngpu = atoi(argv[i + 1]);
+    else if (a == "--mb") mb = (size_t)atol(argv[i + 1]);
+    else if (a == "--reps") reps = atoi(argv[i + 1]);
+    else if (a == "--mode") mode = argv[i + 1];
+    else if (a == "--chunk-mb") chunk_mb = (size_t)atol(argv[i + 1]);
+    else if (a == "--bind") bind = atoi(argv[i + 1]);
+  }
+  int have = 0;
+  cudaGetDeviceCount(&have);
+  if (have < 1) { fprintf(stderr, "no CUDA device\n"); return 1; }
+  if (ngpu > have) ngpu = have;
+  std::vector<std::string> modes = mode == "all" ? std::vector<std::string>{"hostalloc", "wc", "thp"} : std::vector<std::string>{mode};
+  printf("# %d GPU(s) concurrently, %zu MB per direction per GPU x %d reps, chunk %zu MB, bind %d\n", ngpu, mb, reps, chunk_mb, bind);
+  printf("# %-10s %4s %10s %10s %12s %12s %12s\n", "mode", "gpu", "H2D GB/s", "D2H GB/s", "bi H2D GB/s", "bi D2H GB/s", "bi sum GB/s");
+  for (const std::string &m : modes) {
+    std::vector<Result> res(ngpu);
+    pthread_barrier_init(&g_bar, nullptr, ngpu);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpu; ++g) th.emplace_back(worker, g, ngpu, m, mb << 20, chunk_mb << 20, reps, bind != 0, &res[g]);
+    for (auto &t : th) t.join();
+    pthread_barrier_destroy(&g_bar);
+    double s_h2d = 0, s_d2h = 0, s_bi = 0;
+    float slow_h2d = 1e30f, slow_d2h = 1e30f, slow_bi = 0.f;
+    for (int g = 0; g < ngpu; ++g) {
+      const Result &r = res[g];
+      if (!r.ok) { printf("  %-10s %4d   allocation failed\n", m.c_str(), g); continue; }
+      printf("  %-10s %4d %10.1f %10.1f %12.1f %12.1f %12.1f\n", m.c_str(), g, r.h2d, r.d2h, r.bi_h2d, r.bi_d2h, r.bi_h2d + r.bi_d2h);
+      s_h2d += r.h2d; s_d2h += r.d2h; s_bi += r.bi_h2d + r.bi_d2h;
+      slow_h2d = std::min(slow_h2d, r.h2d); slow_d2h = std::min(slow_d2h, r.d2h); slow_bi = std::max(slow_bi, r.bi_wall);
+    }
+    const double bytes = (double)(mb << 20) * reps;
+    printf("  %-10s  sum %10.1f %10.1f %38.1f   | slowest-GPU aggregate: H2D %.1f  D2H %.1f  both %.1f GB/s\n", m.c_str(), s_h2d, s_d2h, s_bi,
+           ngpu * slow_h2d, ngpu * slow_d2h, slow_bi > 0 ? 2.0 * ngpu * bytes / (slow_bi * 1e6) : 0.0);
+  }
   return 0;
 }
