@@ -60,6 +60,8 @@ lib.cloudsc_b200_upload.argtypes = [_vp, _FT, _vp]
 lib.cloudsc_b200_download.argtypes = [_vp, _FT, _vp]
 lib.cloudsc_b200_step.argtypes = [_vp, _d, _i, _i, _vp]
 lib.cloudsc_b200_reset_inout.argtypes = [_vp, _vp]
+lib.cloudsc_b200_set_schedule.argtypes = [_vp, _i, _i, _i]
+lib.cloudsc_b200_set_schedule.restype = _i
 lib.cloudsc_b200_field_ptr.restype = _vp
 lib.cloudsc_b200_field_ptr.argtypes = [_vp, _i]
 lib.cloudsc_b200_sync.argtypes = [_vp]
@@ -202,6 +204,10 @@ class State:
 
     def step(self, ptsphy: float, first_block: int = 0, nblocks: int = 0, stream: int = 0):
         _check(lib.cloudsc_b200_step(self._h, ptsphy, first_block, nblocks, ctypes.c_void_p(stream)))
+
+    def set_schedule(self, mode: int, ksplit: int = 0, target_b: int = 0):
+        """0: one CTA per 32-column tile; 1: persistent warps, upper / lower parts of their tiles interleaved."""
+        _check(lib.cloudsc_b200_set_schedule(self._h, mode, ksplit, target_b))
 
     def reset_inout(self, stream: int = 0):
         _check(lib.cloudsc_b200_reset_inout(self._h, ctypes.c_void_p(stream)))

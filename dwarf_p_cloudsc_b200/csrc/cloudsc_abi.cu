@@ -293,7 +293,7 @@ bool build_tensor_maps(void *const dev[CLOUDSC_NFIELDS], int nblocks, int nproma
   const cuuint64_t np = (cuuint64_t)nproma, kl = (cuuint64_t)klev, nb = (cuuint64_t)nblocks;
   const cuuint64_t rowb = np * es;
   const cuuint64_t dA[4] = {np, kl, nb, 15}, sA[3] = {rowb, kl * rowb, SA};
-  const cuuint32_t bA[4] = {32, 1, 1, 15};
+  const cuuint32_t bA[4] = {32, 1, 1, 15}, bAtop[4] = {32, 1, 1, 7};
   const cuuint64_t dB[4] = {np, kl, nb, 3}, sB[3] = {rowb, kl * rowb, SB};
   const cuuint32_t bB[4] = {32, 1, 1, 3};
   const cuuint64_t dC[5] = {np, kl, 5, nb, 2}, sC[4] = {rowb, kl * rowb, 5 * kl * rowb, SC};
@@ -301,6 +301,7 @@ bool build_tensor_maps(void *const dev[CLOUDSC_NFIELDS], int nblocks, int nproma
   const cuuint64_t dH[3] = {np, kl + 1, nb}, sH[2] = {rowb, (kl + 1) * rowb};
   const cuuint32_t bH[3] = {32, 1, 1};
   return encode_map(&tm->a, precision, dev[kArenaGroupA[0]], 4, dA, sA, bA) &&
+         encode_map(&tm->a_top, precision, dev[kArenaGroupA[0]], 4, dA, sA, bAtop) &&
          encode_map(&tm->b, precision, dev[kArenaGroupB[0]], 4, dB, sB, bB) &&
          encode_map(&tm->c, precision, dev[kArenaGroupC[0]], 5, dC, sC, bC) &&
          encode_map(&tm->h, precision, dev[CLOUDSC_F_PAPH], 3, dH, sH, bH);
@@ -394,7 +395,14 @@ struct cloudsc_b200_state {
   char *arena;                  /* ONE allocation: fields of a kind at a constant spacing (see TensorMaps) */
   TensorMaps tm;
   bool has_tm;                  /* tensor maps encoded: step() uses the 4-requests-per-level TMA kernel */
+  /* persistent schedule (cloudsc_b200_set_schedule): scratch for the state at the cut + per-SM counters */
+  int sched_mode;               /* 0: one CTA per 32-column tile, 1: persistent warps, upper/lower parts interleaved */
+  PersistSchedule sched;
 };
+
+namespace {
+int state_on_current_device(const cloudsc_b200_state *st, const char *what);
+}
 
 int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc_b200_state **out) {
   if (!out) return fail(CLOUDSC_B200_EARG, "create: out is NULL");
@@ -425,7 +433,34 @@ int cloudsc_b200_destroy(cloudsc_b200_state *st) {
   if (!st) return 0;
   if (st->arena) cudaFree(st->arena);
   if (st->plude0) cudaFree(st->plude0);
+  if (st->sched.carry) cudaFree(st->sched.carry);
+  if (st->sched.sm_b) cudaFree(st->sched.sm_b);
   free(st);
+  return 0;
+}
+
+/*
+ * How step() walks the tiles of a launch ("persistent kernel"):
+ *   mode 0  one one-warp CTA per 32-column tile, every tile swept top to bottom in one go
+ *   mode 1  persistent: 12 warps per SM, each running its tiles in two pieces (levels [0, ksplit) and [ksplit, klev))
+ *           and choosing the next piece so that about target_b of the SM's warps are in a lower piece at any time
+ * ksplit <= 0 -> 3*klev/5; target_b <= 0 -> 7 of 12.  Results are bit-identical in every mode.
+ */
+int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b) {
+  if (!st) return fail(CLOUDSC_B200_EARG, "set_schedule: NULL state");
+  if (mode != 0 && mode != 1) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
+  if (ksplit >= st->klev) return fail(CLOUDSC_B200_EARG, "set_schedule: ksplit must be below klev");
+  if (int rc = state_on_current_device(st, "set_schedule")) return rc;
+  if (mode == 1 && st->has_tm && !st->sched.carry) {
+    const int ntiles = (st->nblocks * st->nproma + 31) / 32;
+    CU(cudaMalloc(&st->sched.carry, persist_carry_bytes(ntiles, st->precision)));
+    CU(cudaMalloc((void **)&st->sched.sm_b, 1024 * sizeof(int)));
+    CU(cudaMemset(st->sched.sm_b, 0, 1024 * sizeof(int)));
+    st->sched.carry_tiles = ntiles;
+  }
+  st->sched_mode = mode;
+  st->sched.ksplit = ksplit;
+  st->sched.target_b = target_b;
   return 0;
 }
 
@@ -483,7 +518,9 @@ int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, in
   if (end > st->ngptot) end = st->ngptot;
   LaunchGeom g{first_block * st->nproma, (int)end, st->nproma, st->klev};
   const int variant = g_variant.load();
-  if (st->has_tm && variant == VARIANT_AUTO)
+  if (st->has_tm && variant == VARIANT_AUTO && st->sched_mode == 1)
+    CU(launch_sweep_persist(ft, st->tm, g, ptsphy, st->precision, st->sched, (cudaStream_t)stream));
+  else if (st->has_tm && variant == VARIANT_AUTO)
     CU(launch_sweep_tmap(ft, st->tm, g, ptsphy, st->precision, (cudaStream_t)stream));
   else
     CU(launch_sweep(ft, g, ptsphy, st->precision, variant, (cudaStream_t)stream));
@@ -585,19 +622,24 @@ struct CopyPlan {
 };
 CopyPlan make_copy_plan(int klev, int ncldtop, int aer) {
   CopyPlan p;
-  const size_t ktop = (size_t)(ncldtop > 1 ? ncldtop - 1 : 0);
+  /* $CLOUDSC_B200_E2E_TRIM (measurement knob, tools/gpu_e2e_sweep.py): 2 = default, 1 = species only, 0 = whole fields */
+  const char *env = getenv("CLOUDSC_B200_E2E_TRIM");
+  const int trim = env && *env ? atoi(env) : 2;
+  const size_t ktop = (size_t)(trim >= 2 && ncldtop > 1 ? ncldtop - 1 : 0);
   for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
     p.in0[f] = p.in1[f] = p.out0[f] = p.out1[f] = 0;
     if (is_in(f, aer)) p.in1[f] = rows_of(f, klev);
     if (is_out(f)) p.out1[f] = rows_of(f, klev);
   }
-  p.in1[CLOUDSC_F_PCLV] = p.in1[CLOUDSC_F_TENDENCY_TMP_CLD] = (size_t)4 * klev;
-  p.out1[CLOUDSC_F_TENDENCY_LOC_CLD] = (size_t)4 * klev;
+  if (trim >= 1) {
+    p.in1[CLOUDSC_F_PCLV] = p.in1[CLOUDSC_F_TENDENCY_TMP_CLD] = (size_t)4 * klev;
+    p.out1[CLOUDSC_F_TENDENCY_LOC_CLD] = (size_t)4 * klev;
+  }
   static const int from_ktop[] = {CLOUDSC_F_PQ, CLOUDSC_F_TENDENCY_TMP_Q, CLOUDSC_F_PSUPSAT, CLOUDSC_F_PSNDE, CLOUDSC_F_PHRSW,
                                   CLOUDSC_F_PHRLW, CLOUDSC_F_PVERVEL, CLOUDSC_F_PMFU, CLOUDSC_F_PMFD};
   for (int f : from_ktop) p.in0[f] = ktop < (size_t)klev ? ktop : (size_t)klev;
   p.in0[CLOUDSC_F_PAP] = ktop > 0 ? ktop - 1 : 0;
-  p.in0[CLOUDSC_F_PLU] = ktop + 1 < (size_t)klev ? ktop + 1 : (size_t)klev;
+  p.in0[CLOUDSC_F_PLU] = trim >= 2 ? (ktop + 1 < (size_t)klev ? ktop + 1 : (size_t)klev) : 0;
   for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
     if (is_aer_in(f, aer)) p.in0[f] = ktop < (size_t)klev ? ktop : (size_t)klev;
     if (p.in0[f] > p.in1[f]) p.in0[f] = p.in1[f];

@@ -420,6 +420,14 @@ template <int I, typename T, typename IO> CLOUDSC_FN void park_st(IO &io, T &reg
 #define CLOUDSC_RELOAD 0
 #endif
 
+/* Optional level-range capability of an IO policy (`static constexpr bool kRanged`): the sweep of a column may be cut
+ * into level ranges [k_begin, k_end) run at different times (the persistent kernel interleaves the bandwidth-bound upper
+ * part of one column tile with the latency-bound cloudy part of another).  `Carry` -- and the parked slots -- is exactly
+ * what has to travel across a cut: the policy provides  int k_begin(), k_end();  void load_carry(Carry<T>&),
+ * save_carry(const Carry<T>&).  Every other policy sweeps [0, klev) and none of this is instantiated. */
+template <typename IO, typename = void> struct io_ranged { static constexpr bool value = false; };
+template <typename IO> struct io_ranged<IO, decltype((void)IO::kRanged)> { static constexpr bool value = IO::kRanged; };
+
 /* State carried from level k-1 to level k (what "k-caching" keeps in registers) */
 template <typename T>
 struct Carry {
@@ -519,7 +527,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 #define lcrit_kk (land ? c.rclcrit_land : c.rclcrit_sea)
   (void)r_paph_surf_r;
 
+  int k_begin = 0, k_end = klev;
+  if constexpr (io_ranged<IO>::value) { k_begin = io.k_begin(); k_end = io.k_end(); }
   Carry<T> s;
+  if (k_begin == 0) {
   s.tp1_m1 = zero; s.a_m1 = zero; s.pap_m1 = zero;
   s.paph_k = io.paph_row(0);
   s.mf_k = zero;
@@ -542,8 +553,11 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
   io.template st_row0<OUT_FSQLTUR>(zero); io.template st_row0<OUT_FSQITUR>(zero);
   io.template st_row0<OUT_FPLSL>(zero);  io.template st_row0<OUT_FPLSN>(zero);
   io.template st_row0<OUT_FHPSL>(-c.rlvtt * zero); io.template st_row0<OUT_FHPSN>(-c.rlstt * zero);
+  } else {
+    if constexpr (io_ranged<IO>::value) io.load_carry(s);   /* the sweep resumes below a cut */
+  }
 
-  for (int k = 0; k < klev; ++k) {
+  for (int k = k_begin; k < k_end; ++k) {
     io.level_begin(k);
     /* ================= 1. initial values of this level, :462-485 ========================== */
     const T pap = io.template ld<IN_PAP>(k);
@@ -1302,6 +1316,9 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
     s.tp1_m1 = t; s.a_m1 = a; s.pap_m1 = pap; s.paph_k = paph_n; s.mf_k = mf_n;
     park_st<PARK_PF_I>(io, s.pf_i, pf_i_n); park_st<PARK_PF_R>(io, s.pf_r, pf_r_n); park_st<PARK_PF_S>(io, s.pf_s, pf_s_n);
     io.level_end(k);
+  }
+  if constexpr (io_ranged<IO>::value) {
+    if (k_end < klev) { io.save_carry(s); return; }          /* cut: the rest of the column runs later */
   }
   io.st_rainfrac(park_ld<PARK_RAINFRAC>(io, s.rainfrac));
 }

@@ -306,18 +306,21 @@ cloudsc_sweep_tile(const __grid_constant__ FieldTable ft, const LaunchGeom g, co
  * all fields of a group: 4 requests per level instead of 27.  Same 2-stage ring, same mbarriers, same
  * consumer (one LDS per value) as IO policy 2 with one-warp CTAs.
  */
-const int kArenaGroupA[15] = {CLOUDSC_F_PT, CLOUDSC_F_PQ, CLOUDSC_F_TENDENCY_TMP_T, CLOUDSC_F_TENDENCY_TMP_Q,
-                              CLOUDSC_F_TENDENCY_TMP_A, CLOUDSC_F_PA, CLOUDSC_F_PAP, CLOUDSC_F_PSUPSAT, CLOUDSC_F_PLUDE,
-                              CLOUDSC_F_PSNDE, CLOUDSC_F_PHRSW, CLOUDSC_F_PHRLW, CLOUDSC_F_PVERVEL, CLOUDSC_F_PVFL,
-                              CLOUDSC_F_PVFI};
+/* group a: first the 7 fields every level reads, then the 8 that only the physics levels read (k >= ncldtop - 1; pap one
+ * level earlier): above the cloud-top level one request with the 7-field box `a_top` replaces the 15-field one */
+const int kArenaGroupA[15] = {CLOUDSC_F_PT, CLOUDSC_F_TENDENCY_TMP_T, CLOUDSC_F_TENDENCY_TMP_A, CLOUDSC_F_PA, CLOUDSC_F_PLUDE,
+                              CLOUDSC_F_PVFL, CLOUDSC_F_PVFI,
+                              CLOUDSC_F_PQ, CLOUDSC_F_TENDENCY_TMP_Q, CLOUDSC_F_PAP, CLOUDSC_F_PSUPSAT, CLOUDSC_F_PSNDE,
+                              CLOUDSC_F_PHRSW, CLOUDSC_F_PHRLW, CLOUDSC_F_PVERVEL};
 const int kArenaGroupB[3] = {CLOUDSC_F_PLU, CLOUDSC_F_PMFU, CLOUDSC_F_PMFD};
 const int kArenaGroupC[2] = {CLOUDSC_F_PCLV, CLOUDSC_F_TENDENCY_TMP_CLD};
+constexpr int kGroupATop = 7;   /* fields of group a read at every level */
 
-/* shared-memory row of an input slot: group a rows 0-14, b 15-17, c 18-25 ([field][species]), h 26 */
+/* shared-memory row of an input slot: group a rows 0-14 (kArenaGroupA order), b 15-17, c 18-25 ([field][species]), h 26 */
 __host__ __device__ constexpr int tmap_row(int s) {
-  return s == IN_PT ? 0 : s == IN_PQ ? 1 : s == IN_TT ? 2 : s == IN_TQ ? 3 : s == IN_TA ? 4 : s == IN_PA ? 5
-       : s == IN_PAP ? 6 : s == IN_PSUPSAT ? 7 : s == IN_PLUDE ? 8 : s == IN_PSNDE ? 9 : s == IN_PHRSW ? 10
-       : s == IN_PHRLW ? 11 : s == IN_PVERVEL ? 12 : s == IN_PVFL ? 13 : s == IN_PVFI ? 14
+  return s == IN_PT ? 0 : s == IN_TT ? 1 : s == IN_TA ? 2 : s == IN_PA ? 3 : s == IN_PLUDE ? 4 : s == IN_PVFL ? 5 : s == IN_PVFI ? 6
+       : s == IN_PQ ? 7 : s == IN_TQ ? 8 : s == IN_PAP ? 9 : s == IN_PSUPSAT ? 10 : s == IN_PSNDE ? 11 : s == IN_PHRSW ? 12
+       : s == IN_PHRLW ? 13 : s == IN_PVERVEL ? 14
        : s == IN_PLU ? 15 : s == IN_PMFU ? 16 : s == IN_PMFD ? 17
        : (s >= IN_PCLV0 && s <= IN_PCLV3) ? 18 + (s - IN_PCLV0)
        : (s >= IN_TCLD0 && s <= IN_TCLD3) ? 22 + (s - IN_TCLD0) : 26;
@@ -336,8 +339,19 @@ __device__ __forceinline__ void tma_load_5d(unsigned dst, const CUtensorMap *tm,
                ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-template <typename T>
+/*
+ * RANGED = false: one CTA sweeps levels [0, klev) of one tile (cloudsc_sweep_tmap).
+ * RANGED = true:  the persistent kernel (cloudsc_sweep_persist): the same warp runs level ranges [kb, ke) of several
+ *                 tiles one after the other; the ring's stage / mbarrier-phase bookkeeping continues across them
+ *                 (`kofs` maps a level to the running count of levels this warp has staged), and the state at a cut
+ *                 travels through `carry` (per tile: [kCarryVals][32 lanes] elements, coalesced).
+ */
+constexpr int kCarryRegs = 8;                        /* Carry members that live in registers in the parked code path */
+constexpr int kCarryVals = kCarryRegs + PARK_COUNT;  /* + the parked slots */
+
+template <typename T, bool RANGED = false>
 struct TmapIO {
+  static constexpr bool kRanged = RANGED;
   static constexpr int kCols = 32;
   static constexpr int kRow = kCols * (int)sizeof(T);
   static constexpr int kStage = N_IN * kRow;
@@ -347,22 +361,38 @@ struct TmapIO {
   const TensorMaps &tm;
   int ibl, jl0;                       /* NPROMA block and first column (inside it) of this warp */
   int stride, klev;
+  int ktop1;                          /* ncldtop - 2: levels below it (k < ktop1) read the 7-field box only */
   unsigned smem0, bar0;               /* shared addresses of stage 0 and of full[0] (full[1] at +8) */
   const T *stage_t;                   /* generic pointer: stage 0 + lane */
   const T *cur;
   long long offH, off1;
   unsigned cL, cH1, cC, spstride;     /* 32-bit element offsets of the current level's output rows */
   bool live;                          /* see TileIO::live */
+  /* RANGED only */
+  int kb, ke, kofs;
+  T *carry;                           /* this tile's [kCarryVals][32] block + lane */
+
+  __device__ __forceinline__ int it_of(int level) const { return RANGED ? level + kofs : level; }
+  __device__ __forceinline__ int k_begin() const { return kb; }
+  __device__ __forceinline__ int k_end() const { return ke; }
 
   __device__ __forceinline__ void issue(int level) {   /* one elected lane */
-    const unsigned st = (unsigned)level & 1u;
+    const unsigned st = (unsigned)it_of(level) & 1u;
     const unsigned bar = bar0 + 8u * st;
     const unsigned dst = smem0 + st * (unsigned)kStage;
-    mbar_arrive_expect_tx(bar, (unsigned)kStage);
-    tma_load_4d(dst, &tm.a, bar, jl0, level, ibl, 0);
-    /* row level+1 of plu/pmfu/pmfd does not exist at the last level: the request is out of bounds there,
-       TMA fills zeros (never consumed) and still reports the full box to the mbarrier */
-    tma_load_4d(dst + 15u * kRow, &tm.b, bar, jl0, level + 1, ibl, 0);
+    if (level < ktop1) {
+      /* above the first physics level only 7 of the 15 group-a fields and none of group b are read (cloudsc_column.cuh:
+         qv, the forcing terms and the convective fluxes enter at k >= ncldtop - 1, pap one level earlier); the rows not
+         fetched keep stale values that no output depends on (tests: test_skipped_input_rows_are_dead) */
+      mbar_arrive_expect_tx(bar, (unsigned)((kGroupATop + 8 + 1) * kRow));
+      tma_load_4d(dst, &tm.a_top, bar, jl0, level, ibl, 0);
+    } else {
+      mbar_arrive_expect_tx(bar, (unsigned)kStage);
+      tma_load_4d(dst, &tm.a, bar, jl0, level, ibl, 0);
+      /* row level+1 of plu/pmfu/pmfd does not exist at the last level: the request is out of bounds there,
+         TMA fills zeros (never consumed) and still reports the full box to the mbarrier */
+      tma_load_4d(dst + 15u * kRow, &tm.b, bar, jl0, level + 1, ibl, 0);
+    }
     tma_load_5d(dst + 18u * kRow, &tm.c, bar, jl0, level, 0, ibl, 0);
     tma_load_3d(dst + 26u * kRow, &tm.h, bar, jl0, level + 1, ibl);
   }
@@ -370,21 +400,22 @@ struct TmapIO {
      per level of every 512th CTA into the TENDENCY_CML_T buffer, which the kernel never touches otherwise */
 #ifdef CLOUDSC_TIMING
 #define CLOUDSC_TSTAMP(i)                                                                        \
-  if (threadIdx.x == 0 && blockIdx.x % 512 == 0 && ft.p[CLOUDSC_F_TENDENCY_CML_T])               \
+  if (!RANGED && threadIdx.x == 0 && blockIdx.x % 512 == 0 && ft.p[CLOUDSC_F_TENDENCY_CML_T])    \
     static_cast<long long *>(ft.p[CLOUDSC_F_TENDENCY_CML_T])[(blockIdx.x / 512) * 4 * klev + 4 * k + (i)] = clock64()
 #else
 #define CLOUDSC_TSTAMP(i)
 #endif
   __device__ __forceinline__ void level_begin(int k) {
-    cur = stage_t + (k & 1) * (kStage / (int)sizeof(T));
+    const unsigned it = (unsigned)it_of(k);
+    cur = stage_t + (it & 1u) * (kStage / (int)sizeof(T));
     CLOUDSC_TSTAMP(0);
-    mbar_wait(bar0 + 8u * ((unsigned)k & 1u), ((unsigned)k >> 1) & 1u);
+    mbar_wait(bar0 + 8u * (it & 1u), (it >> 1) & 1u);
     CLOUDSC_TSTAMP(1);
   }
   __device__ __forceinline__ void level_end(int k) {
     CLOUDSC_TSTAMP(2);
     __syncwarp();               /* every lane is done reading stage k&1 */
-    if (k + 2 < klev) {
+    if (k + 2 < (RANGED ? ke : klev)) {
       if (elect_one()) issue(k + 2);
       __syncwarp();
     }
@@ -393,6 +424,21 @@ struct TmapIO {
   }
   __device__ __forceinline__ T &scr(int i) const {
     return const_cast<T *>(stage_t)[(2 * kStage + 32) / (int)sizeof(T) + i * kCols];
+  }
+  /* state at a cut (RANGED): the register members of Carry and every parked slot */
+  __device__ __forceinline__ void save_carry(const Carry<T> &s) {
+    T *c = carry;
+    __stcg(c + 0 * 32, s.tp1_m1); __stcg(c + 1 * 32, s.a_m1); __stcg(c + 2 * 32, s.pap_m1); __stcg(c + 3 * 32, s.paph_k);
+    __stcg(c + 4 * 32, s.mf_k); __stcg(c + 5 * 32, s.anewm1); __stcg(c + 6 * 32, s.qlnm1); __stcg(c + 7 * 32, s.qinm1);
+#pragma unroll
+    for (int i = 0; i < PARK_COUNT; ++i) __stcg(c + (kCarryRegs + i) * 32, scr(i));
+  }
+  __device__ __forceinline__ void load_carry(Carry<T> &s) {
+    const T *c = carry;
+    s.tp1_m1 = __ldcg(c + 0 * 32); s.a_m1 = __ldcg(c + 1 * 32); s.pap_m1 = __ldcg(c + 2 * 32); s.paph_k = __ldcg(c + 3 * 32);
+    s.mf_k = __ldcg(c + 4 * 32); s.anewm1 = __ldcg(c + 5 * 32); s.qlnm1 = __ldcg(c + 6 * 32); s.qinm1 = __ldcg(c + 7 * 32);
+#pragma unroll
+    for (int i = 0; i < PARK_COUNT; ++i) scr(i) = __ldcg(c + (kCarryRegs + i) * 32);
   }
   template <int S> __device__ __forceinline__ T ld(int) const { return cur[tmap_row(S) * kCols]; }
   template <int S> __device__ __forceinline__ T ld_next(int) const { return cur[tmap_row(S) * kCols]; }
@@ -429,12 +475,12 @@ cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant_
   const int jl0 = ccol - ibl * g.nproma;
   const int jl = jl0 + (int)threadIdx.x;
   const long long bL = (long long)ibl * g.klev * g.nproma, bH = (long long)ibl * (g.klev + 1) * g.nproma;
-  IO io{ft, tm, ibl, jl0, g.nproma, g.klev,
+  IO io{ft, tm, ibl, jl0, g.nproma, g.klev, dev_consts<T>().ncldtop - 2,
         smem_u32(smem_raw), smem_u32(smem_raw + 2 * IO::kStage),
         reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
         bH + jl, (long long)ibl * g.nproma + jl,
         (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma),
-        ccol + (int)threadIdx.x < g.col_end};
+        ccol + (int)threadIdx.x < g.col_end, 0, g.klev, 0, nullptr};
   if (threadIdx.x == 0) {
     mbar_init(io.bar0, 1);
     mbar_init(io.bar0 + 8, 1);
@@ -447,6 +493,91 @@ cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant_
   }
   __syncwarp();
   cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+}
+
+/* ---- persistent kernel: every warp walks its own column tiles, upper and lower parts interleaved ------------------- */
+/*
+ * A sweep has two regimes: the levels above the clouds move ~50 rows of IO for a few hundred
+ * instructions and run at the HBM peak once all resident warps are there; the cloudy levels are latency/issue-bound
+ * while HBM idles at ~50 %.  With one CTA per tile all warps start at level 0 together, so the regimes never overlap.
+ * Here the grid is exactly the resident set (12 one-warp CTAs per SM); warp w owns tiles w, w + G, w + 2G, ... and runs
+ * each of them in two pieces, A = levels [0, ksplit) and B = [ksplit, klev), the state at the cut going through
+ * `plan.carry`.  Whenever a warp may choose between the B piece of a tile it has started and the A piece of its next
+ * tile it looks at how many warps of ITS SM are in a B piece right now (a per-SM counter) and takes B only below
+ * `plan.target_b`: the SM then holds a steady mix of bandwidth-bound and latency-bound warps.  There is no dependency
+ * between warps, only that counter; results are bit-identical to the one-CTA-per-tile kernel for any ksplit
+ * (tests/test_cpu_oracle.py::test_cut_sweep_is_bit_identical, tests/test_gpu_parity.py).
+ */
+struct PersistPlan {
+  int ksplit;      /* first level of the B piece, 1 <= ksplit < klev */
+  int ntiles;      /* 32-column tiles of the launch */
+  int target_b;    /* warps per SM that should be in a B piece */
+  void *carry;     /* [ntiles][kCarryVals][32] elements */
+  int *sm_b;       /* per-SM count of warps inside a B piece (self-resetting: +1 / -1 per piece) */
+};
+
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32, warps_per_sm<T>())
+cloudsc_sweep_persist(const __grid_constant__ FieldTable ft, const __grid_constant__ TensorMaps tm, const LaunchGeom g,
+                      const __grid_constant__ StepConst<T> sc, const PersistPlan plan) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using IO = TmapIO<T, true>;
+  const int w = (int)blockIdx.x, G = (int)gridDim.x;
+  if (w >= plan.ntiles) return;
+  const int n_mine = (plan.ntiles - w + G - 1) / G;
+  const unsigned bar0 = smem_u32(smem_raw + 2 * IO::kStage);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  int *const sm_b = plan.sm_b + smid();
+  int a_done = 0, b_done = 0, staged = 0;   /* staged: levels this warp has put through the ring so far */
+  while (b_done < n_mine) {
+    /* which piece next (lane 0 decides, the warp follows) */
+    int do_b = 0;
+    if (threadIdx.x == 0) {
+      const bool can_a = a_done < n_mine, can_b = b_done < a_done;
+      if (!can_a) { do_b = 1; atomicAdd(sm_b, 1); }
+      else if (can_b) {
+        if (atomicAdd(sm_b, 1) < plan.target_b) do_b = 1;
+        else atomicSub(sm_b, 1);
+      }
+    }
+    do_b = __shfl_sync(0xffffffffu, do_b, 0);
+    const int tile = w + (do_b ? b_done : a_done) * G;
+    const int kb = do_b ? plan.ksplit : 0, ke = do_b ? g.klev : plan.ksplit;
+    const int ccol = g.col_begin + tile * IO::kCols;
+    const int ibl = ccol / g.nproma;
+    const int jl0 = ccol - ibl * g.nproma;
+    const int jl = jl0 + (int)threadIdx.x;
+    const long long bL = (long long)ibl * g.klev * g.nproma, bH = (long long)ibl * (g.klev + 1) * g.nproma;
+    const unsigned rows = (unsigned)kb * (unsigned)g.nproma;   /* output offsets start at the piece's first level */
+    IO io{ft, tm, ibl, jl0, g.nproma, g.klev, dev_consts<T>().ncldtop - 2,
+          smem_u32(smem_raw), bar0,
+          reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
+          bH + jl, (long long)ibl * g.nproma + jl,
+          (unsigned)(bL + jl) + rows, (unsigned)(bH + jl + g.nproma) + rows, (unsigned)(bL * 5 + jl) + rows, (unsigned)(g.klev * g.nproma),
+          ccol + (int)threadIdx.x < g.col_end, kb, ke, staged - kb,
+          static_cast<T *>(plan.carry) + (size_t)tile * (kCarryVals * 32) + threadIdx.x};
+    if (elect_one()) {
+      io.issue(kb);
+      if (kb + 1 < ke) io.issue(kb + 1);
+    }
+    __syncwarp();
+    cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+    __syncwarp();             /* all lanes are done with the ring and the scratch before the next piece re-uses them */
+    staged += ke - kb;
+    if (do_b) { ++b_done; if (threadIdx.x == 0) atomicSub(sm_b, 1); }
+    else ++a_done;
+  }
 }
 
 /* ---- IO policy 3: thread-private cp.async ring, pre-offset slot pointers, streaming stores -------- */
@@ -779,6 +910,58 @@ cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const 
                               int precision, cudaStream_t stream) {
   if (precision == CLOUDSC_B200_FP32) return launch_sweep_tmap_t<float>(ft, tm, g, ptsphy, stream);
   return launch_sweep_tmap_t<double>(ft, tm, g, ptsphy, stream);
+}
+
+/* persistent kernel: grid = the resident set (SMs x warps per SM), never more than the tiles */
+template <typename T>
+static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
+                                          const PersistSchedule &ps, cudaStream_t stream) {
+  if (g.col_end <= g.col_begin) return cudaSuccess;
+  const long long nblk = (g.col_end + g.nproma - 1) / g.nproma;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int ntiles = (g.col_end - g.col_begin + 31) / 32;
+  const bool aer = host_consts<T>(dev).laericesed || host_consts<T>(dev).laericeauto;
+  if (aer || nblk * 5 * (g.klev + 1) * g.nproma >= (1ll << 32) || g.klev < 3 || !ps.carry || !ps.sm_b || ntiles > ps.carry_tiles)
+    return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
+  const void *fn = (const void *)cloudsc_sweep_persist<T>;
+  const size_t smem = TmapIO<T, true>::kSmem;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  static int sms[64] = {0}, per_sm[64][2] = {{0}};
+  const int pi = sizeof(T) == 4 ? 1 : 0;
+  if (!sms[dev & 63]) {
+    e = cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+  }
+  if (!per_sm[dev & 63][pi]) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dev & 63][pi], fn, 32, smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int resident = sms[dev & 63] * per_sm[dev & 63][pi];
+  /* fewer tiles than two full rounds of the resident set: nothing to interleave */
+  if (resident <= 0 || ntiles < 2 * resident) return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
+  int ksplit = ps.ksplit > 0 ? ps.ksplit : (3 * g.klev) / 5;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > g.klev - 1) ksplit = g.klev - 1;
+  PersistPlan plan{ksplit, ntiles, ps.target_b > 0 ? ps.target_b : (per_sm[dev & 63][pi] * 7 + 6) / 12, ps.carry, ps.sm_b};
+  StepConst<T> sc;
+  fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
+  void *args[] = {(void *)&ft, (void *)&tm, (void *)&g, (void *)&sc, (void *)&plan};
+  ++g_launches[KERNEL_TMAP];
+  return cudaLaunchKernel(fn, dim3(resident), dim3(32), args, smem, stream);
+}
+
+cudaError_t launch_sweep_persist(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy, int precision,
+                                 const PersistSchedule &ps, cudaStream_t stream) {
+  if (precision == CLOUDSC_B200_FP32) return launch_sweep_persist_t<float>(ft, tm, g, ptsphy, ps, stream);
+  return launch_sweep_persist_t<double>(ft, tm, g, ptsphy, ps, stream);
+}
+size_t persist_carry_bytes(int ntiles, int precision) {
+  return (size_t)ntiles * kCarryVals * 32 * (precision == CLOUDSC_B200_FP32 ? sizeof(float) : sizeof(double));
 }
 
 template <typename T>

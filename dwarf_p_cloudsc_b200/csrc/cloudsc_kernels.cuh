@@ -49,12 +49,13 @@ inline bool variant_valid(int v) {
  * Tensor maps of an ARENA-allocated input set (cloudsc_b200_create): fields of one kind lie at a
  * constant spacing, so ONE tensor-map TMA request fetches the rows of many fields.
  *   a : the 15 [klev] inputs consumed at their own level   box {32 cols, 1 level, 1 block, 15 fields}
+ *   a_top : the same map with a 7-field box (what the levels above the physics read)
  *   b : plu, pmfu, pmfd (consumed one level ahead)          box {32, 1, 1, 3}
  *   c : pclv, tendency_tmp_cld, species 0..3                box {32, 1, 4 species, 1 block, 2 fields}
  *   h : paph                                                box {32, 1, 1}
  */
 struct alignas(64) TensorMaps {
-  CUtensorMap a, b, c, h;
+  CUtensorMap a, a_top, b, c, h;   /* a_top: the first kGroupATop = 7 fields of group a only (levels above the physics) */
 };
 /* order of the fields inside the arena groups (the kernel's shared-memory rows follow it) */
 extern const int kArenaGroupA[15];
@@ -63,6 +64,17 @@ extern const int kArenaGroupC[2];
 
 cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
                               int precision, cudaStream_t stream);
+/* persistent variant of the tensor-map kernel (cloudsc_kernels.cu, "persistent kernel"); falls back to launch_sweep_tmap
+ * for launches with fewer than two rounds of tiles per resident warp.  ksplit / target_b <= 0: defaults. */
+struct PersistSchedule {
+  int ksplit, target_b;
+  void *carry;      /* persist_carry_bytes(carry_tiles, precision) bytes of device scratch */
+  int carry_tiles;
+  int *sm_b;        /* >= 1024 zero-initialised ints of device memory */
+};
+cudaError_t launch_sweep_persist(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy, int precision,
+                                 const PersistSchedule &ps, cudaStream_t stream);
+size_t persist_carry_bytes(int ntiles, int precision);
 cudaError_t tmap_kernel_info(int precision, int out[8]);
 
 cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<float> &c32);

@@ -168,6 +168,10 @@ int cloudsc_b200_upload(cloudsc_b200_state *st, void *const host_fields[CLOUDSC_
 int cloudsc_b200_download(cloudsc_b200_state *st, void *const host_fields[CLOUDSC_NFIELDS], void *stream);
 /* launch over blocks [first_block, first_block+nblocks) of the state; nblocks<=0 -> all */
 int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, int nblocks, void *stream);
+/* how step() schedules the 32-column tiles of a launch: mode 0 = one CTA per tile; mode 1 = persistent warps that run
+ * the upper (bandwidth-bound) and lower (latency-bound) parts of their tiles interleaved, cut at level `ksplit`, with
+ * about `target_b` of an SM's 12 warps in a lower part at any time (<= 0: defaults).  Bit-identical results. */
+int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b);
 /* restore PLUDE from the pristine copy kept at upload() (the kernel scales it in place) */
 int cloudsc_b200_reset_inout(cloudsc_b200_state *st, void *stream);
 /* kernel_info of the kernel step() launches for this state (the arena-backed tensor-map TMA kernel when

@@ -70,6 +70,63 @@ struct HostIOScratch : HostIO<T> {
   T &scr(int i) { return slots[i]; }
 };
 
+/* ... and with the level-range capability of the persistent kernel: the sweep of a column is cut at given levels, the
+ * state at a cut (Carry registers + parked slots) goes through a buffer, and the scratch is poisoned in between -- what
+ * another column tile occupying the warp's shared memory in the meantime would do to it. */
+template <typename T>
+struct HostIORanged : HostIOScratch<T> {
+  static constexpr bool kRanged = true;
+  int kb, ke;
+  T *buf;   /* 8 + PARK_COUNT values */
+  int k_begin() const { return kb; }
+  int k_end() const { return ke; }
+  void save_carry(const Carry<T> &s) {
+    buf[0] = s.tp1_m1; buf[1] = s.a_m1; buf[2] = s.pap_m1; buf[3] = s.paph_k; buf[4] = s.mf_k; buf[5] = s.anewm1;
+    buf[6] = s.qlnm1; buf[7] = s.qinm1;
+    for (int i = 0; i < PARK_COUNT; i++) buf[8 + i] = this->slots[i];
+  }
+  void load_carry(Carry<T> &s) {
+    s.tp1_m1 = buf[0]; s.a_m1 = buf[1]; s.pap_m1 = buf[2]; s.paph_k = buf[3]; s.mf_k = buf[4]; s.anewm1 = buf[5];
+    s.qlnm1 = buf[6]; s.qinm1 = buf[7];
+    for (int i = 0; i < PARK_COUNT; i++) this->slots[i] = buf[8 + i];
+  }
+};
+
+template <typename T>
+int run_ranged(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
+               int ngptot, int nproma, int klev, double ptsphy, int cut1, int cut2) {
+  if (check_params(p) || aerosol_mask(p)) return CLOUDSC_B200_EPARAMS;
+  if (!(0 < cut1 && cut1 <= cut2 && cut2 <= klev)) return CLOUDSC_B200_EARG;
+  CloudscConst<T> c;
+  fill_consts<T>(p, k, &c);
+  StepConst<T> sc;
+  fill_step<T>(c, ptsphy, &sc);
+  const int nblocks = (ngptot + nproma - 1) / nproma;
+  const int cuts[4] = {0, cut1, cut2, klev};
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < nblocks; b++) {
+    void *pb[CLOUDSC_NFIELDS];
+    for (int f = 0; f < CLOUDSC_NFIELDS; f++) {
+      const size_t off = (size_t)b * cloudsc_b200_field_block_elems(f, nproma, klev);
+      const size_t es = cloudsc_b200_field_kind(f) == 'I' ? sizeof(int) : sizeof(T);
+      pb[f] = fields[f] ? (void *)((char *)fields[f] + off * es) : nullptr;
+    }
+    const int bsize = (ngptot - b * nproma) < nproma ? (ngptot - b * nproma) : nproma;
+    for (int jl = 0; jl < bsize; jl++) {
+      T buf[8 + PARK_COUNT];
+      for (int r = 0; r < 3; r++) {
+        if (cuts[r] == cuts[r + 1]) continue;
+        HostIORanged<T> io;
+        io.f = pb; io.jl = jl; io.stride = nproma; io.klev = klev;
+        io.kb = cuts[r]; io.ke = cuts[r + 1]; io.buf = buf;
+        for (int i = 0; i < PARK_COUNT; i++) io.slots[i] = T(-1.0e300);
+        cloudsc_column<T>(c, sc, io, klev);
+      }
+    }
+  }
+  return 0;
+}
+
 template <typename T, bool PARKED = false>
 int run(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
         int ngptot, int nproma, int klev, double ptsphy) {
@@ -130,6 +187,10 @@ int cloudsc_emul_blocks_f64(const struct TECLDP *p, const struct cloudsc_consts 
 int cloudsc_emul_blocks_parked_f64(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
                                    int ngptot, int nproma, int klev, double ptsphy) {
   return run<double, true>(p, k, fields, ngptot, nproma, klev, ptsphy);
+}
+int cloudsc_emul_blocks_ranged_f64(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
+                                   int ngptot, int nproma, int klev, double ptsphy, int cut1, int cut2) {
+  return run_ranged<double>(p, k, fields, ngptot, nproma, klev, ptsphy, cut1, cut2);
 }
 int cloudsc_emul_blocks_f32(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
                             int ngptot, int nproma, int klev, double ptsphy) {

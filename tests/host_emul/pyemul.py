@@ -19,7 +19,12 @@ class Emul:
             fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
                            ctypes.c_int, ctypes.c_int, ctypes.c_double]
 
-    def run(self, fields, p, k, ngptot, nproma, klev, ptsphy, dtype=np.float64, parked=False):
+        fn = self.lib.cloudsc_emul_blocks_ranged_f64
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                       ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+
+    def run(self, fields, p, k, ngptot, nproma, klev, ptsphy, dtype=np.float64, parked=False, cuts=None):
         """parked=True: the IO policy has per-thread scratch, so the column code runs the code path of the TMA kernels
         (long-lived state through IO::scr)."""
         from dwarf_p_cloudsc_b200.params import FIELDS
@@ -34,6 +39,11 @@ class Emul:
         if parked:
             assert dtype == np.float64
             fn = self.lib.cloudsc_emul_blocks_parked_f64
-        rc = fn(ctypes.addressof(p), ctypes.addressof(k), tab, ngptot, nproma, klev, ptsphy)
+        if cuts is not None:      # the sweep of every column cut at the two given levels (the persistent kernel's code path)
+            assert dtype == np.float64
+            rc = self.lib.cloudsc_emul_blocks_ranged_f64(ctypes.addressof(p), ctypes.addressof(k), tab, ngptot, nproma, klev,
+                                                         ptsphy, int(cuts[0]), int(cuts[1]))
+        else:
+            rc = fn(ctypes.addressof(p), ctypes.addressof(k), tab, ngptot, nproma, klev, ptsphy)
         if rc:
             raise RuntimeError(f"emulation returned {rc}")

@@ -312,3 +312,32 @@ def test_fast_reference_build_is_the_same_kernel(built, input_data):
         fast.run(B, p, k, 300, 32, klev, scalars["PTSPHY"], 2)
         errs = validate.validate(B, A, 300)
         assert validate.all_pass(errs), (variant, "\n" + validate.format_table(errs))
+
+
+@pytest.mark.parametrize("cuts", [(82, 137), (14, 82), (1, 2), (60, 61), (136, 137), (15, 15)])
+@pytest.mark.parametrize("variant", ["", "warm+land+conv+rain+moist+tend", "sparse+warm+conv"])
+def test_cut_sweep_is_bit_identical(built, oracle, input_data, variant, cuts):
+    """The persistent kernel runs the levels of a column tile in two pieces (bandwidth-bound upper part, latency-bound
+    cloudy part) with other tiles in between; the state at the cut travels through a buffer.  Host build of exactly
+    that code path (IO policy with kRanged, scratch poisoned between the pieces), cut at two arbitrary levels: strict
+    mode bit-identical to the reference, fast mode bit-identical to its own uncut sweep."""
+    import pyemul
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    c2 = state.perturb(cols, variant)
+    ngptot, nproma = 100, 16
+    A = state.blocked_fields(c2, ngptot, nproma, klev)
+    oracle_out = {n: a.copy() for n, a in A.items()}
+    oracle.run(oracle_out, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+    for fast in (False, True):
+        em = pyemul.Emul(fast=fast)
+        whole = {n: a.copy() for n, a in A.items()}
+        em.run(whole, p, k, ngptot, nproma, klev, scalars["PTSPHY"], parked=True)
+        cut = {n: a.copy() for n, a in A.items()}
+        em.run(cut, p, k, ngptot, nproma, klev, scalars["PTSPHY"], cuts=cuts)
+        for f in params.OUTPUT_FIELDS:
+            a, b = state.unblock(whole[f.name], ngptot), state.unblock(cut[f.name], ngptot)
+            assert np.array_equal(a, b), (fast, f.name, float(np.abs(a - b).max()))
+            if not fast:
+                assert np.array_equal(state.unblock(oracle_out[f.name], ngptot), b), f.name

@@ -729,3 +729,37 @@ def test_level0_link_of_the_reference_driver(built, args):
     # per-thread rows: every OpenMP thread made calls
     trows = [l for l in r.stdout.splitlines() if "@ core#" in l]
     assert len(trows) == int(args[0]), r.stdout
+
+
+@pytest.mark.parametrize("ngptot,nproma,perturbation,ksplit,target_b", [(163840, 128, "", 0, 0), (120000, 64, "warm+land+conv+rain+moist+tend", 40, 3),
+                                                                        (131071, 32, "sparse+warm+conv", 136, 12), (114688, 128, "hot+rain+moist+conv", 1, 1)])
+def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma, perturbation, ksplit, target_b):
+    """cloudsc_b200_set_schedule(mode 1): persistent warps that run the upper and lower parts of their column tiles
+    interleaved, the state at the cut going through a device buffer.  Any cut level and any mix target must give the
+    bits of the one-CTA-per-tile kernel (launches big enough for the persistent path: >= 2 tiles per resident warp),
+    incl. a ragged last tile; and the counters say it was the tensor-map family that ran."""
+    from dwarf_p_cloudsc_b200 import params, state, api
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    src = state.perturb(cols, perturbation) if perturbation else cols
+    F = state.blocked_fields(src, ngptot, nproma, klev)
+    api.set_params(p, k)
+    st = api.State(ngptot, nproma, klev)
+    outs = [f.name for f in params.OUTPUT_FIELDS]
+    try:
+        st.upload(F)
+        res = []
+        for mode in (0, 1, 1):
+            st.set_schedule(mode, ksplit, target_b)
+            st.reset_inout()
+            c0 = api.launch_counts()
+            st.step(scalars["PTSPHY"])
+            assert api.launch_counts()["tmap"] == c0["tmap"] + 1
+            G = {n: (np.full_like(F[n], -777.0) if n in outs else F[n]) for n in F}
+            st.download(G); st.sync()
+            res.append(G)
+    finally:
+        st.close()
+    for n in outs:
+        assert np.array_equal(res[0][n], res[1][n]), n
+        assert np.array_equal(res[1][n], res[2][n]), n      # the per-SM counters returned to zero after the first run

@@ -11,11 +11,14 @@ pts = float(scalars["PTSPHY"])
 F = state.blocked_fields(cols, ngptot, nproma, klev)
 H = {n: torch.from_numpy(a).pin_memory() for n, a in F.items()}
 plude0 = H["PLUDE"].clone()
-for chunk, ns in [(0, 0), (54, 4), (107, 4), (160, 4), (320, 4), (54, 3), (107, 3), (107, 6), (54, 8), (27, 8), (214, 2), (320, 2)]:
+for trim in ("2", "1", "0"):     # what travels: rows the kernel reads/writes (default) / species only / whole fields
+  os.environ["CLOUDSC_B200_E2E_TRIM"] = trim
+  print(f"--- CLOUDSC_B200_E2E_TRIM={trim}", flush=True)
+  for chunk, ns in [(0, 0), (54, 4), (107, 4), (107, 3), (160, 3), (214, 2)]:
     ts = []
     for it in range(4):
         H["PLUDE"].copy_(plude0)
         t0 = time.perf_counter()
         st = api.run_host(H, ngptot, nproma, klev, pts, chunk, ns)
         ts.append(1e3 * (time.perf_counter() - t0))
-    print("chunk_blocks %4d nstreams %d : %s ms (kernel sum %.1f ms)" % (chunk, ns, " ".join("%.1f" % x for x in ts), st["kernel_ms"]), flush=True)
+    print("chunk_blocks %4d nstreams %d : %s ms (kernel sum %.1f ms, %.3f + %.3f GB)" % (chunk, ns, " ".join("%.1f" % x for x in ts), st["kernel_ms"], st["h2d_bytes"] / 1e9, st["d2h_bytes"] / 1e9), flush=True)
