@@ -282,6 +282,14 @@ def run_b200(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device (the CLOUDSC hot path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.bind and world > 1:
+        # one slice of the host cores per rank, set BEFORE the host arrays are allocated and first touched
+        ncpu = os.cpu_count() or 1
+        per = max(1, ncpu // world)
+        try:
+            os.sched_setaffinity(0, set(range(local_rank * per, min(ncpu, (local_rank + 1) * per))))
+        except OSError as exc:
+            log(f"[rank {rank}] sched_setaffinity failed: {exc}")
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -302,9 +310,16 @@ def run_b200(args, rank, local_rank, world):
     t_setup = time.time()
     first_column, _ = shard.weak_shard(rank, world, ngptot)
     F = state.blocked_fields(cols, ngptot, nproma, klev, first_column=first_column)
-    H = {}
+    H, keep = {}, []
     for n in list(F):                                                   # pinned host copies (e2e inputs), one field at a time
-        H[n] = torch.from_numpy(F.pop(n)).pin_memory()
+        a = F.pop(n)
+        if args.pin == "torch":
+            H[n] = torch.from_numpy(a).pin_memory()
+        else:                   # the library's own allocator: plain cudaHostAlloc, or 2 MB pages first-touched by this rank
+            hb = api.HostBuffer(a.shape, a.dtype, api.HOST_HUGEPAGES if args.pin == "thp" else 0)
+            hb.array[...] = a
+            keep.append(hb)
+            H[n] = torch.from_numpy(hb.array)
     del F
     stream = torch.cuda.current_stream().cuda_stream
     # resident device state of the library (cloudsc_b200_create/upload/step): one arena, tensor-map TMA.
@@ -414,6 +429,9 @@ def run_b200(args, rank, local_rank, world):
                "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_t, "steps": e2e_steps,
                "step_ms": [round(x, 2) for x in per_step], "kernel_ms_sum_rank0": round(kern_ms, 3),
                "gb_per_s_per_gpu": (h2d + d2h) / (e2e_t * 1e-3) / 1e9, "validated_vs_reference_h5": e2e_ok,
+               "host_memory": {"torch": "torch pin_memory (cudaHostAlloc)", "hostalloc": "cloudsc_b200_host_alloc_ex(0)",
+                               "thp": "cloudsc_b200_host_alloc_ex(HUGEPAGES): 2 MB pages, first touch by the rank, cudaHostRegister"}[args.pin],
+               "rank_core_binding": bool(args.bind and world > 1),
                "api": "cloudsc_b200_run_host (C ABI, pinned host fields, chunked multi-stream H2D|kernel|D2H; only the rows the kernel reads/writes travel)"}
 
     # -- the reference's own CUDA kernels on the same device, same fields, same timing protocol (N=1 only)
@@ -488,6 +506,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel sweeps only)")
+    ap.add_argument("--pin", default="torch", choices=["torch", "hostalloc", "thp"],
+                    help="page-locked host arrays of the e2e leg: torch pin_memory, the library's cudaHostAlloc, or 2 MB pages + cudaHostRegister")
+    ap.add_argument("--bind", type=int, default=0, help="1: pin every rank to its own slice of the host cores before allocating")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA kernels (N=1 leg)")
     ap.add_argument("--gpu-reference-steps", type=int, default=10)
     args = ap.parse_args()

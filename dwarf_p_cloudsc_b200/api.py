@@ -69,6 +69,10 @@ lib.cloudsc_b200_set_variant.argtypes = [_i]
 lib.cloudsc_b200_state_kernel_info.argtypes = [_vp, ctypes.POINTER(ctypes.c_int * 8)]
 lib.cloudsc_b200_state_kernel_info.restype = _i
 lib.cloudsc_c.argtypes = [_i, _i, _i, _i, _d] + [_vp] * NFIELDS
+lib.cloudsc_b200_host_alloc_ex.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_uint]
+lib.cloudsc_b200_host_alloc_ex.restype = _i
+lib.cloudsc_b200_host_free.argtypes = [_vp]
+lib.cloudsc_b200_host_free.restype = _i
 lib.cloudsc_b200_launch_counts.argtypes = [ctypes.POINTER(ctypes.c_longlong * 5)]
 for _n in ("set_params", "launch", "kernel_info", "launch_counts", "run_host", "run_host_ex", "release_thread", "release_cache", "create", "destroy", "upload", "download",
            "step", "reset_inout", "sync", "set_variant", "get_variant", "device_count",
@@ -151,6 +155,27 @@ def launch_counts() -> Dict[str, int]:
     out = (ctypes.c_longlong * 5)()
     _check(lib.cloudsc_b200_launch_counts(out))
     return dict(zip(KERNEL_FAMILIES, (int(x) for x in out)))
+
+
+HOST_WRITE_COMBINED, HOST_HUGEPAGES = 1, 2
+
+
+class HostBuffer:
+    """Page-locked host memory from the library (cloudsc_b200_host_alloc_ex), viewed as a NumPy array."""
+
+    def __init__(self, shape, dtype, flags: int = 0):
+        import numpy as np
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = ctypes.c_void_p()
+        _check(lib.cloudsc_b200_host_alloc_ex(ctypes.byref(self._p), self.nbytes, flags))
+        buf = (ctypes.c_char * max(self.nbytes, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib.cloudsc_b200_host_free(self._p)
+            self._p = ctypes.c_void_p()
 
 
 def release_cache() -> None:

@@ -14,6 +14,8 @@
 #include <mutex>
 #include <vector>
 
+#include <sys/mman.h>
+
 #include <cuda_runtime.h>
 
 #include "cloudsc_b200.h"
@@ -168,8 +170,50 @@ int cloudsc_b200_host_alloc(void **out, size_t bytes) {
   return 0;
 }
 
+namespace {
+/* blocks handed out by host_alloc_ex(CLOUDSC_B200_HOST_HUGEPAGES): malloc'ed + registered, not cudaHostAlloc'ed */
+std::mutex g_reg_mu;
+std::vector<void *> g_registered;
+}  // namespace
+
+int cloudsc_b200_host_alloc_ex(void **out, size_t bytes, unsigned flags) {
+  if (!out) return fail(CLOUDSC_B200_EARG, "host_alloc_ex: out is NULL");
+  *out = nullptr;
+  if (!bytes) bytes = 1;
+  if (flags & CLOUDSC_B200_HOST_HUGEPAGES) {
+    /* 2 MB-aligned anonymous memory, transparent huge pages requested, touched by THIS thread (first touch places
+       the pages on the caller's NUMA node), then page-locked */
+    const size_t align = (size_t)2 << 20, n = (bytes + align - 1) / align * align;
+    void *p = aligned_alloc(align, n);
+    if (!p) return fail(CLOUDSC_B200_ENOMEM, "host_alloc_ex: out of host memory (%zu bytes)", n);
+    madvise(p, n, MADV_HUGEPAGE);
+    for (size_t o = 0; o < n; o += 4096) ((volatile char *)p)[o] = 0;
+    cudaError_t e = cudaHostRegister(p, n, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { free(p); return cuda_fail(e, "cudaHostRegister"); }
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    g_registered.push_back(p);
+    *out = p;
+    return 0;
+  }
+  unsigned f = cudaHostAllocPortable;
+  if (flags & CLOUDSC_B200_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+  CU(cudaHostAlloc(out, bytes, f));
+  return 0;
+}
+
 int cloudsc_b200_host_free(void *p) {
-  if (p) CU(cudaFreeHost(p));
+  if (!p) return 0;
+  {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (size_t i = 0; i < g_registered.size(); ++i)
+      if (g_registered[i] == p) {
+        g_registered.erase(g_registered.begin() + (long)i);
+        cudaHostUnregister(p);
+        free(p);
+        return 0;
+      }
+  }
+  CU(cudaFreeHost(p));
   return 0;
 }
 
@@ -726,6 +770,9 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     if (e != cudaSuccess) { pipe.release(); return cuda_fail(e, "run_host: pipeline resources"); }
   }
   const int variant = g_variant.load();
+  /* $CLOUDSC_B200_E2E_COPIES_ONLY=1 (tools/gpu_e2e_sweep.py): skip the kernel launches, to time the transfers alone */
+  const char *co_env = getenv("CLOUDSC_B200_E2E_COPIES_ONLY");
+  const bool copies_only = co_env && *co_env == '1';
   for (int i = 0; i < nstreams; ++i) {
     Lane &l = pipe.lanes[i];
     if (l.tm_blocks != chunk_blocks || l.tm_nproma != nproma || l.tm_klev != klev || l.tm_precision != precision || l.tm_aer != aer) {
@@ -779,7 +826,8 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     if (cend > ngptot) cend = ngptot;
     LaunchGeom g{0, (int)(cend - (long long)b0 * nproma), nproma, klev};
     CUX(cudaEventRecord(l.k0, l.stream));
-    if (l.has_tm && variant == VARIANT_AUTO) CUX(launch_sweep_tmap(ft, l.tm, g, ptsphy, precision, l.stream));
+    if (copies_only) { /* measurement knob: the copy pipeline alone (outputs are then meaningless) */ }
+    else if (l.has_tm && variant == VARIANT_AUTO) CUX(launch_sweep_tmap(ft, l.tm, g, ptsphy, precision, l.stream));
     else CUX(launch_sweep(ft, g, ptsphy, precision, variant, l.stream));
     CUX(cudaEventRecord(l.k1, l.stream));
     /* downloads: whole blocks, except that of a ragged last block only the columns the caller's run covers come

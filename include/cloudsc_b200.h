@@ -100,6 +100,11 @@ int cloudsc_b200_set_device(int device);
 /* page-locked host memory for the field arrays (what makes H2D/D2H asynchronous; the reference
  * driver uses plain malloc, cloudsc_driver.c:119-179) -- or pin memory the caller already owns */
 int cloudsc_b200_host_alloc(void **out, size_t bytes);
+/* flags: WRITE_COMBINED = uncached on the CPU side (upload-only buffers: the device reads them without snooping);
+ * HUGEPAGES = 2 MB pages (transparent huge pages) first-touched by the calling thread, then page-locked: 512x fewer
+ * IOMMU translations per byte and NUMA placement by the caller's affinity.  Free either kind with host_free(). */
+enum { CLOUDSC_B200_HOST_WRITE_COMBINED = 1, CLOUDSC_B200_HOST_HUGEPAGES = 2 };
+int cloudsc_b200_host_alloc_ex(void **out, size_t bytes, unsigned flags);
 int cloudsc_b200_host_free(void *p);
 int cloudsc_b200_host_register(void *p, size_t bytes);
 int cloudsc_b200_host_unregister(void *p);

@@ -11,10 +11,12 @@ pts = float(scalars["PTSPHY"])
 F = state.blocked_fields(cols, ngptot, nproma, klev)
 H = {n: torch.from_numpy(a).pin_memory() for n, a in F.items()}
 plude0 = H["PLUDE"].clone()
-for trim in ("2", "1", "0"):     # what travels: rows the kernel reads/writes (default) / species only / whole fields
+MODES = [("2", "0"), ("2", "1")] if "--quick" in sys.argv else [("2", "0"), ("2", "1"), ("1", "0"), ("0", "0")]
+for trim, copies_only in MODES:  # what travels: rows the kernel reads/writes (default) / species only / whole fields
   os.environ["CLOUDSC_B200_E2E_TRIM"] = trim
-  print(f"--- CLOUDSC_B200_E2E_TRIM={trim}", flush=True)
-  for chunk, ns in [(0, 0), (54, 4), (107, 4), (107, 3), (160, 3), (214, 2)]:
+  os.environ["CLOUDSC_B200_E2E_COPIES_ONLY"] = copies_only
+  print(f"--- CLOUDSC_B200_E2E_TRIM={trim} COPIES_ONLY={copies_only}", flush=True)
+  for chunk, ns in [(0, 0), (54, 4), (107, 3), (27, 4), (14, 8)]:
     ts = []
     for it in range(4):
         H["PLUDE"].copy_(plude0)
