@@ -597,6 +597,7 @@ constexpr int kMaxLanes = 8;
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
+  cudaEvent_t up = nullptr, down = nullptr;   /* ring mode: inputs uploaded / outputs downloaded (arena free again) */
   char *arena = nullptr;
   size_t bytes = 0;             /* size of `arena` */
   bool used = false;
@@ -609,12 +610,20 @@ struct Pipe {
   std::mutex mu;
   Lane lanes[kMaxLanes];
   cudaEvent_t w0 = nullptr, w1 = nullptr;
+  /* ring mode: ONE stream per copy direction and one for the kernels, the lanes' arenas as a ring of buffers */
+  cudaStream_t s_up = nullptr, s_k = nullptr, s_down = nullptr;
   void release() {
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_k) cudaStreamDestroy(s_k);
+    if (s_down) cudaStreamDestroy(s_down);
+    s_up = s_k = s_down = nullptr;
     for (int i = 0; i < kMaxLanes; ++i) {
       Lane &l = lanes[i];
       if (l.arena) cudaFree(l.arena);
       if (l.k0) cudaEventDestroy(l.k0);
       if (l.k1) cudaEventDestroy(l.k1);
+      if (l.up) cudaEventDestroy(l.up);
+      if (l.down) cudaEventDestroy(l.down);
       if (l.stream) cudaStreamDestroy(l.stream);
       l = Lane();
     }
@@ -631,6 +640,9 @@ cudaError_t pipe_reserve(Pipe &p, int nlanes, size_t lane_bytes) {
   if (!p.w0) {
     if ((e = cudaEventCreate(&p.w0)) != cudaSuccess) return e;
     if ((e = cudaEventCreate(&p.w1)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&p.s_up, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&p.s_k, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&p.s_down, cudaStreamNonBlocking)) != cudaSuccess) return e;
   }
   for (int i = 0; i < nlanes; ++i) {
     Lane &l = p.lanes[i];
@@ -638,6 +650,8 @@ cudaError_t pipe_reserve(Pipe &p, int nlanes, size_t lane_bytes) {
       if ((e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
       if ((e = cudaEventCreate(&l.k0)) != cudaSuccess) return e;
       if ((e = cudaEventCreate(&l.k1)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&l.up, cudaEventDisableTiming)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&l.down, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
     if (!l.arena || l.bytes < lane_bytes) {
       if (l.arena) { cudaFree(l.arena); l.arena = nullptr; l.bytes = 0; }
@@ -646,6 +660,7 @@ cudaError_t pipe_reserve(Pipe &p, int nlanes, size_t lane_bytes) {
       l.has_tm = false; l.tm_blocks = 0;
       /* rows of the inputs the kernel never reads are never uploaded (CopyPlan): give them a defined value once */
       if ((e = cudaMemsetAsync(l.arena, 0, lane_bytes, l.stream)) != cudaSuccess) return e;
+      if ((e = cudaStreamSynchronize(l.stream)) != cudaSuccess) return e;   /* (the ring mode uses other streams) */
     }
     l.used = false;
   }
@@ -791,6 +806,7 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     cudaError_t e_ = (call);                                         \
     if (e_ != cudaSuccess) {                                         \
       for (int i_ = 0; i_ < nstreams; ++i_) cudaStreamSynchronize(pipe.lanes[i_].stream); \
+      cudaStreamSynchronize(pipe.s_up); cudaStreamSynchronize(pipe.s_k); cudaStreamSynchronize(pipe.s_down); \
       return cuda_fail(e_, #call);                                   \
     }                                                                \
   } while (0)
@@ -805,31 +821,41 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     for (size_t r = 0; r < (size_t)klev; ++r) memset(cov + r * rowb[CLOUDSC_F_PCOVPTOT] + (size_t)valid_last * es, 0, (size_t)(nproma - valid_last) * es);
     for (size_t r = 0; r < (size_t)4 * klev; ++r) memset(cld + r * rowb[CLOUDSC_F_TENDENCY_LOC_CLD] + (size_t)valid_last * es, 0, (size_t)(nproma - valid_last) * es);
   }
+  /* Stream layout.  ring (default): ONE upload stream, ONE kernel stream, ONE download stream; the lanes' arenas form
+     a ring of buffers handed from stream to stream by events -- each copy engine is fed by a single in-order queue,
+     as in the two-stream copy micro-benchmark (tools/ubench/pcie.cu).  lanes ($CLOUDSC_B200_E2E_PIPE=lanes, the
+     round-1 layout): every lane has its own stream carrying upload, kernel and download of its chunks. */
+  const char *pipe_env = getenv("CLOUDSC_B200_E2E_PIPE");
+  const bool ring = !(pipe_env && strcmp(pipe_env, "lanes") == 0);
   int b0 = 0;
   for (int c = 0; c < nchunks; ++c) {
     Lane &l = pipe.lanes[c % nstreams];
     const int nb = sizes[c];
+    cudaStream_t s_up = ring ? pipe.s_up : l.stream, s_k = ring ? pipe.s_k : l.stream, s_down = ring ? pipe.s_down : l.stream;
     if (l.used) {  /* harvest the kernel time of the chunk that used this lane before */
       CUX(cudaEventSynchronize(l.k1));
       float ms = 0.f;
       CUX(cudaEventElapsedTime(&ms, l.k0, l.k1));
       kernel_ms += ms;
+      if (ring) CUX(cudaStreamWaitEvent(s_up, l.down, 0));   /* the arena is free once its outputs are on the host */
     }
     FieldTable ft;
     for (int f = 0; f < CLOUDSC_NFIELDS; ++f) ft.p[f] = is_live(f, aer) ? l.arena + lay.off[f] : nullptr;
     for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
       if (plan.in1[f] <= plan.in0[f]) continue;
       CUX(copy_rows((char *)ft.p[f], (const char *)host[f] + (size_t)b0 * blk[f], blk[f], rowb[f], plan.in0[f], plan.in1[f], nb,
-                    cudaMemcpyHostToDevice, l.stream, &h2d));
+                    cudaMemcpyHostToDevice, s_up, &h2d));
     }
+    if (ring) { CUX(cudaEventRecord(l.up, s_up)); CUX(cudaStreamWaitEvent(s_k, l.up, 0)); }
     long long cend = (long long)(b0 + nb) * nproma;
     if (cend > ngptot) cend = ngptot;
     LaunchGeom g{0, (int)(cend - (long long)b0 * nproma), nproma, klev};
-    CUX(cudaEventRecord(l.k0, l.stream));
+    CUX(cudaEventRecord(l.k0, s_k));
     if (copies_only) { /* measurement knob: the copy pipeline alone (outputs are then meaningless) */ }
-    else if (l.has_tm && variant == VARIANT_AUTO) CUX(launch_sweep_tmap(ft, l.tm, g, ptsphy, precision, l.stream));
-    else CUX(launch_sweep(ft, g, ptsphy, precision, variant, l.stream));
-    CUX(cudaEventRecord(l.k1, l.stream));
+    else if (l.has_tm && variant == VARIANT_AUTO) CUX(launch_sweep_tmap(ft, l.tm, g, ptsphy, precision, s_k));
+    else CUX(launch_sweep(ft, g, ptsphy, precision, variant, s_k));
+    CUX(cudaEventRecord(l.k1, s_k));
+    if (ring) CUX(cudaStreamWaitEvent(s_down, l.k1, 0));
     /* downloads: whole blocks, except that of a ragged last block only the columns the caller's run covers come
        back (the reference leaves the padding columns of its outputs untouched) */
     const bool has_ragged = ragged && b0 + nb == nblocks;
@@ -837,15 +863,16 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
       if (plan.out1[f] <= plan.out0[f]) continue;
       CUX(copy_rows((char *)host[f] + (size_t)b0 * blk[f], (const char *)ft.p[f], blk[f], rowb[f], plan.out0[f], plan.out1[f], nfull,
-                    cudaMemcpyDeviceToHost, l.stream, &d2h));
+                    cudaMemcpyDeviceToHost, s_down, &d2h));
       if (has_ragged) {
         const size_t es = elem_size(f, precision), w = (size_t)valid_last * es, rows = plan.out1[f] - plan.out0[f];
         CUX(cudaMemcpy2DAsync((char *)host[f] + (size_t)(nblocks - 1) * blk[f] + plan.out0[f] * rowb[f], rowb[f],
                               (const char *)ft.p[f] + (size_t)nfull * blk[f] + plan.out0[f] * rowb[f], rowb[f], w, rows,
-                              cudaMemcpyDeviceToHost, l.stream));
+                              cudaMemcpyDeviceToHost, s_down));
         d2h += w * rows;
       }
     }
+    if (ring) CUX(cudaEventRecord(l.down, s_down));
     l.used = true;
     b0 += nb;
   }
@@ -857,6 +884,7 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     char *cld = (char *)host[CLOUDSC_F_TENDENCY_LOC_CLD];
     for (int b = 0; b < nblocks; ++b) memset(cld + (size_t)b * blk[CLOUDSC_F_TENDENCY_LOC_CLD] + 4 * sp, 0, sp);
   }
+  if (ring) { CUX(cudaStreamSynchronize(pipe.s_down)); CUX(cudaStreamSynchronize(pipe.s_k)); CUX(cudaStreamSynchronize(pipe.s_up)); }
   for (int i = 0; i < nstreams; ++i) {
     Lane &l = pipe.lanes[i];
     CUX(cudaStreamSynchronize(l.stream));
