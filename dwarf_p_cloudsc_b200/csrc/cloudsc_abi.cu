@@ -15,6 +15,7 @@
 #include <vector>
 
 #include <sys/mman.h>
+#include <time.h>
 
 #include <cuda_runtime.h>
 
@@ -587,6 +588,11 @@ void *cloudsc_b200_field_ptr(cloudsc_b200_state *st, int f) {
 /* host-resident fields: chunked multi-stream pipeline                                            */
 /* ---------------------------------------------------------------------------------------------- */
 namespace {
+double wall_now() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 /*
  * Per-device pipeline resources, kept between calls: cudaMalloc/cudaFree cost ~1 ms / ~0.4 ms each on
  * B200 (tools/ubench/pcie.cu), which for 51 fields x 3 lanes would be twice the time the copies
@@ -746,8 +752,11 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     if (chunk_blocks < min_blocks) chunk_blocks = min_blocks;
     if (chunk_blocks > nblocks) chunk_blocks = nblocks;
     int left = nblocks;
+    /* quarter- and half-size chunks at both ends: the first upload and the last download overlap with nothing
+       (measured 3.7 + 2.3 ms of a 110 ms call with full-size end chunks, profiles/r2_e2e_trace.txt) */
     const int q = chunk_blocks / 4, h = chunk_blocks / 2;
-    if (q >= min_blocks && left > 4 * chunk_blocks) {
+    const int ramp_floor = (1024 + nproma - 1) / nproma;
+    if (q >= ramp_floor && left > 4 * chunk_blocks) {
       sizes.push_back(q); sizes.push_back(h);
       left -= q + h;
       const int tail = q + h;
@@ -827,6 +836,17 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
      round-1 layout): every lane has its own stream carrying upload, kernel and download of its chunks. */
   const char *pipe_env = getenv("CLOUDSC_B200_E2E_PIPE");
   const bool ring = !(pipe_env && strcmp(pipe_env, "lanes") == 0);
+  /* $CLOUDSC_B200_E2E_TRACE=1: time line of the call on stderr (per chunk: upload / kernel / download begin and end on
+     the device, host-side phases), for tools/gpu_e2e_sweep.py --trace */
+  const char *tr_env = getenv("CLOUDSC_B200_E2E_TRACE");
+  const bool trace = tr_env && *tr_env == '1' && nchunks <= 96;
+  std::vector<cudaEvent_t> tev;
+  if (trace) {
+    tev.resize((size_t)nchunks * 6);
+    for (auto &e : tev) cudaEventCreate(&e);
+  }
+  const double host_t0 = wall_now();
+  double host_enq = 0.0, host_memset = 0.0;
   int b0 = 0;
   for (int c = 0; c < nchunks; ++c) {
     Lane &l = pipe.lanes[c % nstreams];
@@ -841,11 +861,13 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     }
     FieldTable ft;
     for (int f = 0; f < CLOUDSC_NFIELDS; ++f) ft.p[f] = is_live(f, aer) ? l.arena + lay.off[f] : nullptr;
+    if (trace) cudaEventRecord(tev[(size_t)c * 6 + 0], s_up);
     for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
       if (plan.in1[f] <= plan.in0[f]) continue;
       CUX(copy_rows((char *)ft.p[f], (const char *)host[f] + (size_t)b0 * blk[f], blk[f], rowb[f], plan.in0[f], plan.in1[f], nb,
                     cudaMemcpyHostToDevice, s_up, &h2d));
     }
+    if (trace) cudaEventRecord(tev[(size_t)c * 6 + 1], s_up);
     if (ring) { CUX(cudaEventRecord(l.up, s_up)); CUX(cudaStreamWaitEvent(s_k, l.up, 0)); }
     long long cend = (long long)(b0 + nb) * nproma;
     if (cend > ngptot) cend = ngptot;
@@ -856,6 +878,7 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     else CUX(launch_sweep(ft, g, ptsphy, precision, variant, s_k));
     CUX(cudaEventRecord(l.k1, s_k));
     if (ring) CUX(cudaStreamWaitEvent(s_down, l.k1, 0));
+    if (trace) { cudaEventRecord(tev[(size_t)c * 6 + 2], s_k); cudaEventRecord(tev[(size_t)c * 6 + 3], s_down); }
     /* downloads: whole blocks, except that of a ragged last block only the columns the caller's run covers come
        back (the reference leaves the padding columns of its outputs untouched) */
     const bool has_ragged = ragged && b0 + nb == nblocks;
@@ -872,10 +895,12 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
         d2h += w * rows;
       }
     }
+    if (trace) cudaEventRecord(tev[(size_t)c * 6 + 4], s_down);
     if (ring) CUX(cudaEventRecord(l.down, s_down));
     l.used = true;
     b0 += nb;
   }
+  host_enq = wall_now() - host_t0;
   /* species 4 (vapour) of TENDENCY_LOC_CLD is never written by the kernel and never downloaded: it holds the
      zeros of cloudsc_driver.c:200.  Written here, by the otherwise idle calling thread, while the copies run. */
   {
@@ -884,6 +909,7 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
     char *cld = (char *)host[CLOUDSC_F_TENDENCY_LOC_CLD];
     for (int b = 0; b < nblocks; ++b) memset(cld + (size_t)b * blk[CLOUDSC_F_TENDENCY_LOC_CLD] + 4 * sp, 0, sp);
   }
+  host_memset = wall_now() - host_t0;
   if (ring) { CUX(cudaStreamSynchronize(pipe.s_down)); CUX(cudaStreamSynchronize(pipe.s_k)); CUX(cudaStreamSynchronize(pipe.s_up)); }
   for (int i = 0; i < nstreams; ++i) {
     Lane &l = pipe.lanes[i];
@@ -899,6 +925,17 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
   float wall = 0.f;
   CUX(cudaEventElapsedTime(&wall, pipe.w0, pipe.w1));
   if (stats) { stats[0] = (double)h2d; stats[1] = (double)d2h; stats[2] = kernel_ms; stats[3] = wall; }
+  if (trace) {
+    fprintf(stderr, "run_host trace: %d chunks, %d buffers, %s; host: enqueue done %.2f ms, species-5 zeroing done %.2f ms, all done %.2f ms\n",
+            nchunks, nstreams, ring ? "ring" : "lanes", 1e3 * host_enq, 1e3 * host_memset, 1e3 * (wall_now() - host_t0));
+    fprintf(stderr, "  chunk blocks |  upload begin..end  | kernel end | download begin..end   [ms since the first upload began]\n");
+    for (int c = 0; c < nchunks; ++c) {
+      float t[5] = {0, 0, 0, 0, 0};
+      for (int j = 0; j < 5; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[(size_t)c * 6 + j]);
+      fprintf(stderr, "  %5d %6d | %8.2f .. %8.2f | %8.2f | %8.2f .. %8.2f\n", c, sizes[c], t[0], t[1], t[2], t[3], t[4]);
+    }
+    for (auto &e : tev) cudaEventDestroy(e);
+  }
 #undef CUX
   return 0;
 }

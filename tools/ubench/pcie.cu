@@ -103,8 +103,39 @@ static void worker(int g, int ngpu, const std::string &mode, size_t n, size_t ch
   cudaFree(d_up); cudaFree(d_dn);
 }
 
+// --pattern 1: the access pattern of cloudsc_b200_run_host on ONE GPU: `nin` separate upload arrays and `nout` separate
+// download arrays of `mb` MB each, walked chunk by chunk (one copy of chunk_mb MB per array per chunk; uploads on one
+// stream, downloads on another, no dependencies), against the same bytes moved as two flat buffers.
+static void pattern(const std::string &mode, size_t arr_bytes, size_t chunk, int nin, int nout) {
+  cudaSetDevice(0);
+  std::vector<char *> hin(nin), hout(nout);
+  for (auto &p : hin) p = (char *)alloc_host(mode, arr_bytes, true);
+  for (auto &p : hout) p = (char *)alloc_host(mode, arr_bytes, false);
+  char *d_up, *d_dn;
+  const size_t ring = 4 * chunk * (size_t)std::max(nin, nout);
+  cudaMalloc(&d_up, ring); cudaMalloc(&d_dn, ring);
+  cudaStream_t s1, s2; cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+  cudaEvent_t a1, b1, a2, b2; cudaEventCreate(&a1); cudaEventCreate(&b1); cudaEventCreate(&a2); cudaEventCreate(&b2);
+  const int nchunks = (int)(arr_bytes / chunk);
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(a1, s1); cudaEventRecord(a2, s2);
+    for (int c = 0; c < nchunks; ++c) {
+      char *du = d_up + (size_t)(c % 4) * chunk * nin, *dd = d_dn + (size_t)(c % 4) * chunk * nout;
+      for (int f = 0; f < nin; ++f) cudaMemcpyAsync(du + (size_t)f * chunk, hin[f] + (size_t)c * chunk, chunk, cudaMemcpyHostToDevice, s1);
+      for (int f = 0; f < nout; ++f) cudaMemcpyAsync(hout[f] + (size_t)c * chunk, dd + (size_t)f * chunk, chunk, cudaMemcpyDeviceToHost, s2);
+    }
+    cudaEventRecord(b1, s1); cudaEventRecord(b2, s2);
+    cudaEventSynchronize(b1); cudaEventSynchronize(b2);
+    float m1, m2; cudaEventElapsedTime(&m1, a1, b1); cudaEventElapsedTime(&m2, a2, b2);
+    const double up = (double)nin * nchunks * chunk, dn = (double)nout * nchunks * chunk;
+    printf("  pattern %-9s rep %d: %d+%d arrays x %zu MB in %zu-KB pieces: H2D %.2f GB in %.1f ms (%.1f GB/s), D2H %.2f GB in %.1f ms (%.1f GB/s), sum %.1f GB/s over %.1f ms\n",
+           mode.c_str(), rep, nin, nout, arr_bytes >> 20, chunk >> 10, up / 1e9, m1, up / m1 / 1e6, dn / 1e9, m2, dn / m2 / 1e6,
+           (up + dn) / std::max(m1, m2) / 1e6, std::max(m1, m2));
+  }
+}
+
 int main(int argc, char **argv) {
-  int ngpu = 1, reps = 3, bind = 0;
+  int ngpu = 1, reps = 3, bind = 0, pat = 0, nin = 35, nout = 22;
   size_t mb = 1024, chunk_mb = 0;
   std::string mode = "all";
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -115,11 +146,19 @@ int main(int argc, char **argv) {
     else if (a == "--mode") mode = argv[i + 1];
     else if (a == "--chunk-mb") chunk_mb = (size_t)atol(argv[i + 1]);
     else if (a == "--bind") bind = atoi(argv[i + 1]);
+    else if (a == "--pattern") pat = atoi(argv[i + 1]);
+    else if (a == "--nin") nin = atoi(argv[i + 1]);
+    else if (a == "--nout") nout = atoi(argv[i + 1]);
   }
   int have = 0;
   cudaGetDeviceCount(&have);
   if (have < 1) { fprintf(stderr, "no CUDA device\n"); return 1; }
   if (ngpu > have) ngpu = have;
+  if (pat) {
+    for (const std::string &m : (mode == "all" ? std::vector<std::string>{"hostalloc", "thp"} : std::vector<std::string>{mode}))
+      pattern(m, mb << 20, (chunk_mb ? chunk_mb : 8) << 20, nin, nout);
+    return 0;
+  }
   std::vector<std::string> modes = mode == "all" ? std::vector<std::string>{"hostalloc", "wc", "thp"} : std::vector<std::string>{mode};
   printf("# %d GPU(s) concurrently, %zu MB per direction per GPU x %d reps, chunk %zu MB, bind %d\n", ngpu, mb, reps, chunk_mb, bind);
   printf("# %-10s %4s %10s %10s %12s %12s %12s\n", "mode", "gpu", "H2D GB/s", "D2H GB/s", "bi H2D GB/s", "bi D2H GB/s", "bi sum GB/s");
