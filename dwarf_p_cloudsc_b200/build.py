@@ -68,13 +68,13 @@ def build_library(force=False, verbose=False, extra_nvcc=()):
 
 def build_driver(force=False, verbose=False):
     srcs = [os.path.join(HOST, f) for f in ("dwarf_cloudsc.c", "cloudsc_driver.c", "load_state.c",
-                                            "cloudsc_validate.c", "h5lite.c", "mycpu.c")]
+                                            "cloudsc_validate.c", "h5lite.c", "mycpu.c", "ec_pmon.c")]
     if not all(os.path.exists(s) for s in srcs):
         return None
     headers = _glob(HOST, (".h",)) + _glob(INC, (".h",))
     if force or _newer(DRIVER, srcs + headers + [LIB]):
         _run([HOSTCC, "-std=c11", "-O2", "-fopenmp", f"-I{INC}", f"-I{HOST}", *srcs, "-o", DRIVER,
-              f"-L{LIBDIR}", "-lcloudsc_b200", f"-Wl,-rpath,$ORIGIN", "-lm"], verbose)
+              f"-L{LIBDIR}", "-lcloudsc_b200", f"-Wl,-rpath,$ORIGIN", "-lm", "-ldl"], verbose)
     return DRIVER
 
 

@@ -16,6 +16,7 @@
 
 #include <omp.h>
 
+#include "ec_pmon.h"
 #include "mycpu.h"
 
 static int g_status = 0;
@@ -36,7 +37,7 @@ static void *pinned(size_t bytes) {
   void *p = NULL;
   if (cloudsc_b200_host_alloc(&p, bytes) != 0) {
     fprintf(stderr, "cloudsc_driver: cannot allocate %zu bytes of page-locked memory: %s\n", bytes, cloudsc_b200_last_error());
-    exit(2);
+    return NULL;   /* the caller reports the failure through cloudsc_driver_status(); a driver routine never exits */
   }
   return p;
 }
@@ -64,9 +65,17 @@ void cloudsc_driver(int numthreads, int numcols, int nproma) {
 
   /* every field of the cloudsc_c() argument list, sized as the reference sizes it; the kernel never
    * touches the N/A fields but the driver contract allocates and loads them, so we do too */
+  for (int f = 0; f < CLOUDSC_NFIELDS; ++f) F[f] = NULL;
   for (int f = 0; f < CLOUDSC_NFIELDS; ++f) {
     const size_t elems = (size_t)nblocks * cloudsc_b200_field_block_elems(f, nproma, nlev);
     F[f] = pinned(elems * (cloudsc_b200_field_kind(f) == 'I' ? sizeof(int) : sizeof(double)));
+    if (!F[f]) {
+      g_status = CLOUDSC_B200_ENOMEM;
+      for (int q = 0; q < f; ++q) cloudsc_b200_host_free(F[q]);
+      free(yrecldp);
+      yrecldp = NULL;
+      return;
+    }
   }
 #define P(name) ((double *)F[CLOUDSC_F_##name])
   load_state(klon, nlev, nclv, numcols, nproma, &ptsphy, P(PLCRIT_AER), P(PICRIT_AER), P(PRE_ICE), P(PCCN), P(PNICE),
@@ -76,6 +85,11 @@ void cloudsc_driver(int numthreads, int numcols, int nproma) {
              (int *)F[CLOUDSC_F_KTYPE], P(PLU), P(PLUDE), P(PSNDE), P(PMFU), P(PMFD), P(PA), P(PCLV), P(PSUPSAT));
 
   double zinfo[5][MAXGPU];
+  /* EC_PMON=1 (as upstream, cloudsc_driver_mod.F90:113-114): energy and power of every GPU over a sustained run of the
+     sweep -- one 2 ms sweep is far below the update period of the counters, so the sweep is repeated for ~1 s before
+     the timed launch (PLUDE restored every time), the power sampled every 16th sweep as upstream samples every 100th block */
+  const int lec_pmon = ec_pmon_init();
+  double pmon[5][MAXGPU];   /* joules, seconds, sweeps, max W, sum of sampled W (count in [2]/16) */
   int failed = 0;
   const double t0 = omp_get_wtime();
   double t_kernel_begin = 0.0, t_kernel_end = 0.0;
@@ -103,6 +117,27 @@ void cloudsc_driver(int numthreads, int numcols, int nproma) {
       CK(cloudsc_b200_step(st, ptsphy, 0, 0, NULL));   /* warm-up launch (module load, clocks) */
       CK(cloudsc_b200_reset_inout(st, NULL));          /* PLUDE is in/out: restore it for the timed run */
       CK(cloudsc_b200_sync(NULL));
+      pmon[0][tid] = pmon[1][tid] = pmon[2][tid] = pmon[3][tid] = pmon[4][tid] = 0.0;
+      if (lec_pmon && !failed) {
+        double e0 = 0.0, e1 = 0.0, w = 0.0;
+        ec_pmon(tid, &e0, &w);
+        const double p0 = omp_get_wtime();
+        int sweeps = 0, samples = 0;
+        while (omp_get_wtime() - p0 < 1.0 && !failed) {
+          for (int r = 0; r < 16 && !failed; ++r) {
+            CK(cloudsc_b200_step(st, ptsphy, 0, 0, NULL));
+            CK(cloudsc_b200_reset_inout(st, NULL));
+            ++sweeps;
+          }
+          CK(cloudsc_b200_sync(NULL));
+          ec_pmon(tid, &e1, &w);
+          if (w > pmon[3][tid]) pmon[3][tid] = w;
+          pmon[4][tid] += w;
+          ++samples;
+        }
+        pmon[0][tid] = e1 - e0; pmon[1][tid] = omp_get_wtime() - p0; pmon[2][tid] = (double)sweeps;
+        if (samples) pmon[4][tid] /= samples;
+      }
     }
 #pragma omp barrier
 #pragma omp master
@@ -159,6 +194,21 @@ void cloudsc_driver(int numthreads, int numcols, int nproma) {
     printf(" %10d%10d%10d%10d%10d %4d : %10d%10d%10d END2END (create + H2D + warm-up + sweep + D2H) time_us=%.1f\n", numthreads,
            numcols, numcols, nblocks, nproma, -2, (int)(tall * 1000. + 0.5), (int)(1.0e-06 * zhpm * ((double)numcols / 100.) / tall),
            (int)((double)numcols / tall), tall * 1.0e6);
+  }
+
+  if (lec_pmon) {
+    double pmax = 0.0, psum = 0.0, joules = 0.0, sweeps = 0.0;
+    for (int t = 0; t < numthreads; ++t) {
+      printf(" Power usage gpu#%d :: energy: %.1f J over %.0f sweeps in %.3f s = %.3f J/sweep (%.1f W); sampled power max: %.1f W avg: %.1f W\n", t,
+             pmon[0][t], pmon[2][t], pmon[1][t], pmon[2][t] > 0 ? pmon[0][t] / pmon[2][t] : 0.0, pmon[1][t] > 0 ? pmon[0][t] / pmon[1][t] : 0.0,
+             pmon[3][t], pmon[4][t]);
+      if (pmon[3][t] > pmax) pmax = pmon[3][t];
+      psum += pmon[4][t]; joules += pmon[0][t]; sweeps += pmon[2][t];
+    }
+    /* the reference's line (cloudsc_driver_mod.F90:197-199), watts summed over the GPUs */
+    printf(" Power usage (sampled):: max: %.0f avg: %.1f count: %d ; energy per column: %.3e J\n", pmax * numthreads, psum, numthreads,
+           sweeps > 0 ? joules / (sweeps * ((double)numcols / numthreads)) : 0.0);
+    ec_pmon_shutdown();
   }
 
   cloudsc_validate(klon, nlev, nclv, numcols, nproma, P(PLUDE), P(PCOVPTOT), P(PRAINFRAC_TOPRFZ), P(PFSQLF), P(PFSQIF),

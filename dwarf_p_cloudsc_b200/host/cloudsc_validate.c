@@ -22,13 +22,15 @@ int cloudsc_validate_failures(void) { return g_failures; }
 
 static void validate_field(const char *name, const double *ref, const double *field, int nproma, int rows, int ngptot, int nblocks) {
   double vmin = DBL_MAX, vmax = -DBL_MAX, maxerr = 0.0, errsum = 0.0, refsum_int = 0.0, refsum = 0.0, refmax = 0.0;
-#pragma omp parallel for schedule(static) reduction(min : vmin) reduction(max : vmax, maxerr, refmax) reduction(+ : errsum, refsum_int, refsum)
+  long nonfinite = 0;   /* fmin/fmax drop NaN, and a field whose reference is all zero is judged on maxerr alone: count them */
+#pragma omp parallel for schedule(static) reduction(min : vmin) reduction(max : vmax, maxerr, refmax) reduction(+ : errsum, refsum_int, refsum, nonfinite)
   for (int b = 0; b < nblocks; ++b) {
     const int bsize = nproma < ngptot - b * nproma ? nproma : ngptot - b * nproma;   /* valid columns of the block */
     for (int r = 0; r < rows; ++r) {
       const size_t o = ((size_t)b * rows + r) * nproma;
       for (int i = 0; i < bsize; ++i) {
         const double v = field[o + i], w = ref[o + i], d = fabs(v - w);
+        if (!isfinite(v)) ++nonfinite;
         vmin = fmin(vmin, v);
         vmax = fmax(vmax, v);
         maxerr = fmax(maxerr, d);
@@ -47,8 +49,9 @@ static void validate_field(const char *name, const double *ref, const double *fi
   else { rel = errsum / refsum_int; iopt = 3; }
   const char *warn = rel > 10.0 * eps ? " !!!!" : "     ";
   const double l1 = refsum > 0.0 ? errsum / refsum : (errsum > 0.0 ? INFINITY : 0.0);
-  const int pass = (refsum > 0.0 ? l1 <= 1.0e-10 && maxerr <= 1.0e-9 * refmax : maxerr <= 1.0e-14);
+  const int pass = nonfinite == 0 && isfinite(errsum) && (refsum > 0.0 ? l1 <= 1.0e-10 && maxerr <= 1.0e-9 * refmax : maxerr <= 1.0e-14);
   if (!pass) ++g_failures;
+  if (nonfinite) fprintf(stderr, "cloudsc_validate: %s holds %ld non-finite value(s)\n", name, nonfinite);
   printf(" %20s %dD%d %20.13le %20.13le %20.13le %20.13le %20.13le %s %14.5le %s\n", name, 2, iopt, vmin, vmax, maxerr,
          errsum / (double)ngptot, 100.0 * rel, warn, 100.0 * l1, pass ? "PASS" : "FAIL");
 }
@@ -64,7 +67,11 @@ void cloudsc_validate(const int nlon, const int nlev, const int nclv, const int 
   /* one slab for the 21 reference fields, carved in the order of the argument list */
   const size_t total = 5 * n2 /* plude pcovptot a q t */ + n1 + 14 * n2h + n3;
   double *slab = malloc(sizeof(double) * total);
-  if (!slab) { fprintf(stderr, "cloudsc_validate: out of memory\n"); exit(2); }
+  if (!slab) {   /* never exit() from a library-facing routine: report every field as failed */
+    fprintf(stderr, "cloudsc_validate: out of memory (%zu bytes for the reference fields)\n", sizeof(double) * total);
+    g_failures = 21;
+    return;
+  }
   double *p = slab;
 #define CARVE(n) (p += (n), p - (n))
   double *r_plude = CARVE(n2), *r_pcovptot = CARVE(n2), *r_rainfrac = CARVE(n1);

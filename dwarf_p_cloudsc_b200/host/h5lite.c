@@ -137,7 +137,7 @@ void h5lite_close(h5lite_file *f) {
 size_t h5lite_count(const h5lite_file *f) { return f->nent; }
 const char *h5lite_name(const h5lite_file *f, size_t i) { return i < f->nent ? f->ent[i].name : NULL; }
 
-struct dsctx { const h5lite_file *f; h5lite_dataset d; int have_space, have_type, have_layout; size_t esize; };
+struct dsctx { const h5lite_file *f; h5lite_dataset d; int have_space, have_type, have_layout; size_t esize; uint64_t layout_bytes; };
 static int dataset_msg(void *ctx, unsigned type, const unsigned char *b, unsigned size) {
   struct dsctx *c = ctx;
   if (type == 0x0001 && size >= 4) {                 /* dataspace v1/v2 */
@@ -164,8 +164,13 @@ static int dataset_msg(void *ctx, unsigned type, const unsigned char *b, unsigne
       uint64_t a = rd(b + 2, 8), n = rd(b + 10, 8);
       if (a == UINT64_MAX) c->d.data = NULL;
       else { if (!in_range(c->f, c->f->base + a, n)) return fail("dataset outside the file"); c->d.data = c->f->buf + c->f->base + a; }
+      c->layout_bytes = n;
     } else if (b[1] == 0) {
+      /* compact: 2-byte size, then the data inside this message */
+      const uint64_t n = rd(b + 2, 2);
+      if (n + 4 > size) return fail("compact dataset larger than its layout message");
       c->d.data = b + 4;
+      c->layout_bytes = n;
     } else return fail("chunked layout not supported");
     c->have_layout = 1;
   }
@@ -181,6 +186,13 @@ int h5lite_find(const h5lite_file *f, const char *name, h5lite_dataset *out) {
     c.f = f;
     if (for_messages(f, f->ent[i].ohdr, dataset_msg, &c)) return -1;
     if (!c.have_space || !c.have_type || !c.have_layout) return fail("object is not a simple dataset");
+    /* the element count comes from the dataspace, the bytes that exist from the layout: a truncated or inconsistent
+       file must fail here, not read past the data */
+    if (c.d.data && (c.esize == 0 || c.d.count > c.layout_bytes / c.esize)) {
+      snprintf(g_err, sizeof g_err, "dataset %s: dataspace (%zu elements of %zu bytes) exceeds its storage (%llu bytes)", name,
+               c.d.count, c.esize, (unsigned long long)c.layout_bytes);
+      return -1;
+    }
     *out = c.d;
     return 0;
   }

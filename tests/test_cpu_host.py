@@ -187,3 +187,63 @@ def test_validate_replicated_equals_the_plain_validator():
             assert a.name == b.name
             for x, y in zip(a[1:], b[1:]):
                 assert x == y or abs(x - y) <= 1e-12 * max(abs(x), abs(y)), (ngptot, nproma, a.name, a, b)
+
+
+def test_c_validate_fails_on_nan_in_an_all_zero_field(hostlib, capfd):
+    """fmin/fmax drop NaN, and a field whose reference is identically zero (PFPLSL, PFHPSL in the data set) is judged
+    on max|err| alone: a NaN there must still FAIL."""
+    from dwarf_p_cloudsc_b200 import state
+    ngptot, nproma, klev = 100, 50, 137
+    ref = state.load_reference()
+    order = ["PLUDE", "PCOVPTOT", "PRAINFRAC_TOPRFZ", "PFSQLF", "PFSQIF", "PFCQLNG", "PFCQNNG", "PFSQRF", "PFSQSF",
+             "PFCQRNG", "PFCQSNG", "PFSQLTUR", "PFSQITUR", "PFPLSL", "PFPLSN", "PFHPSL", "PFHPSN", "TENDENCY_LOC_A",
+             "TENDENCY_LOC_Q", "TENDENCY_LOC_T", "TENDENCY_LOC_CLD"]
+    F = {n: state.expand(ref[n], ngptot, nproma) for n in order}
+    assert not F["PFPLSL"].any()
+    F["PFPLSL"][1, 7, 3] = np.nan
+    F["PFHPSL"][...] = np.nan
+    hostlib.cloudsc_validate(100, klev, 5, ngptot, nproma, *[_ptr(F[n]) for n in order])
+    cap = capfd.readouterr()
+    assert hostlib.cloudsc_validate_failures() == 2
+    bad = sorted(l.split()[0] for l in cap.out.splitlines() if "FAIL" in l)
+    assert bad == ["PFHPSL", "PFPLSL"], cap.out
+    assert "non-finite" in cap.err
+
+
+def test_c_h5lite_rejects_a_truncated_or_inconsistent_file(hostlib, tmp_path):
+    """Element counts come from the dataspace, the bytes that exist from the layout message: a file cut short, or one
+    whose dataspace claims more elements than its storage holds, is refused instead of read out of bounds."""
+    from dwarf_p_cloudsc_b200 import h5lite
+    rng = np.random.default_rng(3)
+    a = rng.random((7, 100))
+    good = tmp_path / "good.h5"
+    h5lite.write_h5(str(good), {"A": a, "N": np.array([5], dtype=np.int32)})
+    raw = bytearray(good.read_bytes())
+    out = np.empty(a.size)
+    f = hostlib.h5lite_open(str(good).encode())
+    assert f and hostlib.h5lite_read_double(f, b"A", out.ctypes.data_as(_dp), a.size) == 0 and np.array_equal(out, a.reshape(-1))
+    hostlib.h5lite_close(f)
+    # (1) cut the file in the middle of A's data
+    cut = tmp_path / "cut.h5"
+    pos = bytes(raw).find(a.tobytes())
+    assert pos > 0
+    cut.write_bytes(bytes(raw[:pos + a.nbytes // 2]))
+    f = hostlib.h5lite_open(str(cut).encode())
+    if f:
+        assert hostlib.h5lite_read_double(f, b"A", out.ctypes.data_as(_dp), a.size) == -1
+        hostlib.h5lite_close(f)
+    # (2) dataspace of A claims 7 x 200 elements, its contiguous storage still holds 7 x 100
+    import struct
+    bad = bytearray(raw)
+    dims = struct.pack("<QQ", 7, 100)
+    i = bytes(bad).find(dims)
+    assert i > 0
+    bad[i:i + 16] = struct.pack("<QQ", 7, 200)
+    lie = tmp_path / "lie.h5"
+    lie.write_bytes(bytes(bad))
+    f = hostlib.h5lite_open(str(lie).encode())
+    assert f
+    big = np.empty(1400)
+    assert hostlib.h5lite_read_double(f, b"A", big.ctypes.data_as(_dp), 1400) == -1
+    assert b"exceeds its storage" in hostlib.h5lite_error()
+    hostlib.h5lite_close(f)

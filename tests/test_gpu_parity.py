@@ -769,3 +769,28 @@ def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma,
             assert np.array_equal(res[0][n], res[1][n]), n
     errs = validate.validate(res[1], res[0], ngptot)
     assert validate.all_pass(errs) and max(e.rel_l1 for e in errs) < 1e-14, "\n" + validate.format_table(errs)
+
+
+def test_c_driver_power_sampling(built):
+    """EC_PMON=1 (the reference's switch, ec_pmon_mod.F90:14-57 / cloudsc_driver_mod.F90:113-118,197-199): the C driver
+    reports energy and sampled power of the GPU over a sustained run of the sweep (NVML, dlopen'ed), and still validates."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "dwarf_p_cloudsc_b200", "lib", "dwarf-cloudsc-b200")
+    env = dict(os.environ, EC_PMON="1")
+    r = subprocess.run([exe, "1", "65536", "128"], cwd=os.path.join(root, "tests", "golden"), capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    m = re.search(r"Power usage \(sampled\):: max: (\d+) avg: ([\d.]+) count: (\d+)", r.stdout)
+    assert m, r.stdout
+    per = re.search(r"Power usage gpu#0 :: energy: ([\d.]+) J over (\d+) sweeps in ([\d.]+) s", r.stdout)
+    assert per and int(per.group(2)) >= 16 and float(per.group(3)) >= 0.9, r.stdout
+    if float(m.group(1)) > 0:          # NVML present on the box: a B200 under load draws well over 100 W
+        assert 50.0 < float(m.group(2)) < 1500.0 and float(per.group(1)) > 10.0, r.stdout
+    rows = [l for l in r.stdout.splitlines() if " 2D" in l]
+    assert len(rows) == 21 and all(l.rstrip().endswith("PASS") for l in rows), r.stdout
+    # without the switch: no power lines
+    r = subprocess.run([exe, "1", "1000", "100"], cwd=os.path.join(root, "tests", "golden"), capture_output=True, text=True, timeout=600,
+                       env={k: v for k, v in os.environ.items() if k != "EC_PMON"})
+    assert r.returncode == 0 and "Power usage" not in r.stdout
