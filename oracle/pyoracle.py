@@ -103,6 +103,45 @@ class RefFastOracle(_Oracle):
         super().__init__()
 
 
+class Ref32Oracle:
+    """oracle/_ref/libcloudsc_ref32.so: the unmodified reference kernel re-typed to single precision by the preprocessor
+    (oracle/ref32_wrap.c) -- what a `--single-precision` build of the C dwarf would be.  ``fields`` are float32 arrays
+    (KTYPE int32) in the driver layout; parameters are narrowed from the double-precision objects."""
+    kind = "reference-fp32"
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libcloudsc_ref32.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        os.environ.setdefault("OMP_STACKSIZE", "1G")
+        self.lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
+        self.lib.cloudsc_ref32_blocks.restype = ctypes.c_double
+        self.lib.cloudsc_ref32_blocks.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                  ctypes.POINTER(ctypes.c_void_p)]
+        self.lib.cloudsc_ref32_set_params.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                                      ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                                      ctypes.POINTER(ctypes.c_double)]
+
+    def run(self, fields, p, k, ngptot, nproma, klev, ptsphy, nthreads=0):
+        from dwarf_p_cloudsc_b200.params import FIELDS, KERNEL_CONSTS, TECLDP_INTS, TECLDP_REALS
+        assert self.lib.cloudsc_ref32_sizeof_tecldp() == 4 * (len(TECLDP_REALS) + len(TECLDP_INTS) + 3), "re-typed struct TECLDP layout"
+        reals = (ctypes.c_double * len(TECLDP_REALS))(*[getattr(p, n) for n in TECLDP_REALS])
+        ints = (ctypes.c_int * len(TECLDP_INTS))(*[getattr(p, n) for n in TECLDP_INTS])
+        kk = (ctypes.c_double * len(KERNEL_CONSTS))(*[getattr(k, n) for n in KERNEL_CONSTS])
+        self.lib.cloudsc_ref32_set_params(reals, len(TECLDP_REALS), ints, len(TECLDP_INTS), p.nshapep, p.nshapeq, p.nbeta, kk)
+        tab = (ctypes.c_void_p * len(FIELDS))()
+        for f in FIELDS:
+            a = fields.get(f.name)
+            if a is None:
+                continue
+            assert a.flags["C_CONTIGUOUS"] and a.dtype == (np.int32 if f.kind == "I" else np.float32), f.name
+            tab[f.index] = a.ctypes.data
+        t = self.lib.cloudsc_ref32_blocks(int(nthreads), int(ngptot), int(nproma), int(klev), float(ptsphy), tab)
+        if t < 0:
+            raise ValueError("oracle rejected the arguments")
+        return t
+
+
 class PortOracle(_Oracle):
     libname = "libcloudsc_oracle.so"
     blocks_fn = "cloudsc_oracle_blocks"
