@@ -10,11 +10,15 @@ SURVEY App. C.1), i.e. every |ref| < 1 counts as 0.  We print that reference-com
 true relative L1 error, and judge on the latter:
 
     FP64 bar:   sum|err|/sum|ref| <= 1e-10   and   AbsMaxErr <= 1e-9 * max|ref|
-    FP32 bar (stated here; the reference never validates its SP builds, .github/workflows/build.yml:172):
-        per-field sum|err|/sum|ref| <= FP32_L1_BARS[field] (measured 5e-6 .. 1.2e-1: single precision moves
-        the threshold decisions of the scheme -- rlmin / zepsec = 1e-14 sit far below the FP32 resolution of
-        the mixing ratios they guard -- so whole condensation events appear or vanish at isolated points;
-        the liquid/ice flux sums, which integrate those events down the column, are hit hardest)
+    FP32 (the reference never validates its SP builds, .github/workflows/build.yml:172, so the bars are stated here,
+    from measurement, profiles/r2_fp32_three_way.txt): single precision moves threshold decisions of the scheme
+    (tests like `zqx < rlmin`, `a < ramin`, `zsupsat > zepsec` on values that sit within a few float ulps of the
+    threshold), so whole condensation events appear or vanish at isolated points and the flux sums integrate them down
+    the column.  That is a property of CLOUDSC in FP32, not of this kernel: the reference's own kernel re-typed to
+    float (oracle/_ref32) differs from its FP64 self by up to 1.2e-1 (PFSQLF).  Two bars therefore:
+        "fp32ref"  GPU-FP32 against the CPU-FP32 reference: FP32_L1_BARS_VS_REF32 (measured worst 5e-6 .. 5.4e-2)
+        "fp32"     any FP32 result against the FP64 reference: FP32_L1_BARS (measured worst 5e-6 .. 1.2e-1, for the
+                   device path and for the CPU-FP32 reference alike)
 """
 from __future__ import annotations
 
@@ -29,9 +33,17 @@ FP64_L1_TOL = 1.0e-10
 FP64_MAX_TOL = 1.0e-9
 FP32_L1_TOL = 1.0e-2          # default per-field bar of the FP32 build
 FP32_L1_BARS = {"PFSQLF": 3e-1, "PFSQRF": 3e-1, "PFSQIF": 1e-1, "PFSQSF": 1e-1, "PFCQLNG": 3e-1, "PFCQNNG": 3e-1,
-                "PFCQRNG": 3e-1, "PFCQSNG": 3e-1, "PFPLSN": 2e-2, "PFHPSN": 2e-2, "PFPLSL": 2e-2, "PFHPSL": 2e-2,
+                "PFCQRNG": 3e-1, "PFCQSNG": 3e-1, "PFPLSN": 2e-2, "PFHPSN": 2e-2, "PFPLSL": 8e-2, "PFHPSL": 8e-2,
                 "TENDENCY_LOC_Q": 5e-2, "TENDENCY_LOC_T": 5e-2, "TENDENCY_LOC_CLD": 5e-2, "TENDENCY_LOC_A": 1e-2,
-                "PCOVPTOT": 1e-3, "PLUDE": 1e-4}
+                "PCOVPTOT": 3e-2, "PLUDE": 1e-4}   # (PCOVPTOT, PFPLSL/PFHPSL: set by the synthetic warm-phase input sets)
+
+# GPU-FP32 vs the CPU-FP32 reference (oracle/_ref32): ~3x the worst value measured over the shipped data and three
+# synthetic input sets (profiles/r2_fp32_three_way.txt)
+FP32_L1_BARS_VS_REF32 = {"PLUDE": 1e-6, "PCOVPTOT": 1.5e-2, "PRAINFRAC_TOPRFZ": 1e-6, "PFSQLF": 2e-2, "PFSQRF": 2e-2,
+                         "PFSQIF": 1.2e-2, "PFSQSF": 1.2e-2, "PFCQLNG": 1.5e-1, "PFCQNNG": 1.5e-1, "PFCQRNG": 1.5e-1,
+                         "PFCQSNG": 1.5e-1, "PFSQLTUR": 1e-6, "PFSQITUR": 1e-6, "PFPLSL": 5e-2, "PFHPSL": 5e-2,
+                         "PFPLSN": 1e-2, "PFHPSN": 1e-2, "TENDENCY_LOC_A": 5e-5, "TENDENCY_LOC_Q": 3e-2,
+                         "TENDENCY_LOC_T": 2e-2, "TENDENCY_LOC_CLD": 1.5e-2}
 
 _PRINT_NAME = {"TENDENCY_LOC_A": "TENDENCY_LOC%A", "TENDENCY_LOC_Q": "TENDENCY_LOC%Q",
                "TENDENCY_LOC_T": "TENDENCY_LOC%T", "TENDENCY_LOC_CLD": "TENDENCY_LOC%CLD"}
@@ -57,6 +69,8 @@ class FieldError(NamedTuple):
             return False
         if precision == "fp32":
             return self.rel_l1 <= FP32_L1_BARS.get(self.name, FP32_L1_TOL)
+        if precision == "fp32ref":
+            return self.rel_l1 <= FP32_L1_BARS_VS_REF32.get(self.name, FP32_L1_TOL)
         return self.rel_l1 <= FP64_L1_TOL and self.maxerr <= FP64_MAX_TOL * max(self.refmax, 1e-300)
 
 

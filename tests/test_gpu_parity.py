@@ -26,6 +26,24 @@ def _run_gpu(F, p, k, ngptot, nproma, klev, ptsphy):
     return {n: t.cpu().numpy() for n, t in D.items()}
 
 
+def _check_against_fp32_reference(G, F, p, k, ngptot, nproma, klev, ptsphy):
+    """The FP32 device result against the reference's own kernel re-typed to single precision (oracle/_ref32), per-field
+    bars of validate.FP32_L1_BARS_VS_REF32; the CPU-FP32 reference runs with NPROMA <= 128 (stack temporaries)."""
+    import pyoracle
+    from dwarf_p_cloudsc_b200 import state, validate
+    try:
+        r32 = pyoracle.Ref32Oracle()
+    except (FileNotFoundError, OSError):
+        return
+    onp = min(nproma, 128)
+    cols32 = {n: state.unblock(a, ngptot) for n, a in F.items()}
+    R32 = {n: state.expand(a.astype(np.float32) if a.dtype == np.float64 else a, ngptot, onp) for n, a in cols32.items()}
+    r32.run(R32, p, k, ngptot, onp, klev, ptsphy, 0)
+    errs = [validate.field_error(n, state.unblock(np.asarray(G[n], dtype=np.float64), ngptot),
+                                 state.unblock(R32[n].astype(np.float64), ngptot), ngptot) for n in state.VALIDATE_ORDER]
+    assert validate.all_pass(errs, "fp32ref"), "\n" + validate.format_table(errs, "fp32ref")
+
+
 def _compare(G, R, ngptot, precision="fp64"):
     from dwarf_p_cloudsc_b200 import validate
     errs = validate.validate(G, R, ngptot)
@@ -465,6 +483,7 @@ def test_fp32_build_within_the_stated_single_precision_bars(built, oracle, input
         assert np.isfinite(G[n]).all(), n
     errs = validate.validate(G, R, ngptot)
     assert validate.all_pass(errs, "fp32"), "\n" + validate.format_table(errs, "fp32")
+    _check_against_fp32_reference(G, F, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
 
 
 @pytest.mark.parametrize("ngptot,nproma", [(1000, 128), (4099, 64), (777, 96)])
@@ -496,6 +515,7 @@ def test_fp32_resident_state_within_the_single_precision_bars(built, oracle, inp
         assert np.isfinite(G[n]).all(), n
     errs = validate.validate(G, R, ngptot)
     assert validate.all_pass(errs, "fp32"), "\n" + validate.format_table(errs, "fp32")
+    _check_against_fp32_reference(G, F, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
     # same arithmetic through caller-owned float fields
     D = {n: torch.from_numpy(a.astype(np.float32) if a.dtype == np.float64 else a).cuda() for n, a in F.items()}
     api.launch(D, ngptot, nproma, klev, scalars["PTSPHY"], precision=api.FP32)
