@@ -40,7 +40,7 @@ def built():
     if os.path.exists(os.path.join(ROOT, "oracle", "cloudsc_oracle.c")):
         targets.append("port")
     if os.path.exists("/root/reference/src/cloudsc_c/cloudsc/cloudsc_c.c"):
-        targets += ["ref", "ref32", "reffast", "level0"]
+        targets += ["ref", "ref32", "reffast", "cpuref", "level0"]
     if os.path.exists("/root/reference/src/cloudsc_cuda/cloudsc/cloudsc_c_k_caching.cu"):
         targets.append("gpuref")
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), *targets], check=True, stdout=subprocess.DEVNULL)
