@@ -482,6 +482,116 @@ CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
 }
 
 /*
+ * 5.2 sink limiter, cloudsc_c.c:2233-2286, on the antisymmetric representation of ZSOLQA (a_xy = zsolqa[x][y] for
+ * x < y, diagonal d_m; species 0=l 1=i 2=r 3=s 4=v; the pair (i,s) and d_v are never written by any process).
+ * (The first pass :2207-2227 is overwritten before use.)  zratio = zmm/max(zsinksum,zmm) is exactly 1 unless the sinks
+ * of species m exceed its content, and scaling by 1 is the identity -- so the divide and the scaling only run in that
+ * case.  Returns the column sums cs_m = sum_n zsolqa[n][m] of the limited matrix, i.e. the explicit terms of :2330.
+ */
+template <typename T>
+CLOUDSC_FN void sink_limiter(const CloudscConst<T> &c, T &a01, T &a02, T &a03, T &a04, T &a12, T &a14, T &a23, T &a24, T &a34,
+                             T &d0, T &d1, T &d2, T &d3, const T (&qx)[4], const T qv, T &cs0, T &cs1, T &cs2, T &cs3, T &cs4) {
+  const T zero = T(0.0);
+      /* column sums sum_n zsolqa[n][m], n = 0..4 in the reference's order (:2239, :2330) */
+#define CLOUDSC_COLSUM0 ((((zero + d0) - a01) - a02) - a03) - a04
+#define CLOUDSC_COLSUM1 (((zero + a01) + d1) - a12) - a14
+#define CLOUDSC_COLSUM2 ((((zero + a02) + a12) + d2) - a23) - a24
+#define CLOUDSC_COLSUM3 (((zero + a03) + a23) + d3) - a34
+#define CLOUDSC_COLSUM4 (((zero + a04) + a14) + a24) + a34
+      /* "if zsolqa[n][m] < 0 scale the pair": a_nm itself for n < m, a_mn > 0 for n > m; a negative
+       * diagonal is scaled twice (n == m hits both statements of :2281-2282) */
+#define CLOUDSC_SCALE_LO(a) if ((a) < zero) (a) = (a) * ratio
+#define CLOUDSC_SCALE_HI(a) if ((a) > zero) (a) = (a) * ratio
+#define CLOUDSC_SCALE_D(d) if ((d) < zero) (d) = ((d) * ratio) * ratio
+      /* The five species are limited one after the other (a scaled pair feeds the later column sums),
+       * but when no column exceeds its content -- the common case -- nothing is scaled at all and the
+       * five unscaled sums are also the explicit sums of :2330.  So: all five sums and tests up front
+       * (independent chains), and the sequential pass only if one of them fires; by induction over m
+       * the pass cannot fire unless one of the up-front tests does. */
+      cs0 = CLOUDSC_COLSUM0; cs1 = CLOUDSC_COLSUM1; cs2 = CLOUDSC_COLSUM2; cs3 = CLOUDSC_COLSUM3; cs4 = CLOUDSC_COLSUM4;
+      const T mm0 = mx(qx[0], c.zepsec), mm1 = mx(qx[1], c.zepsec), mm2 = mx(qx[2], c.zepsec), mm3 = mx(qx[3], c.zepsec),
+              mm4 = mx(qv, c.zepsec);
+      if (CLOUDSC_RARE((zero - cs0 > mm0) | (zero - cs1 > mm1) | (zero - cs2 > mm2) | (zero - cs3 > mm3) | (zero - cs4 > mm4))) {
+        T sinksum = zero - cs0;
+        if (sinksum > mm0) {
+          const T ratio = CLOUDSC_DIV(mm0, sinksum);
+          CLOUDSC_SCALE_D(d0); CLOUDSC_SCALE_HI(a01); CLOUDSC_SCALE_HI(a02); CLOUDSC_SCALE_HI(a03); CLOUDSC_SCALE_HI(a04);
+        }
+        sinksum = zero - (CLOUDSC_COLSUM1);
+        if (sinksum > mm1) {
+          const T ratio = CLOUDSC_DIV(mm1, sinksum);
+          CLOUDSC_SCALE_LO(a01); CLOUDSC_SCALE_D(d1); CLOUDSC_SCALE_HI(a12); CLOUDSC_SCALE_HI(a14);
+        }
+        sinksum = zero - (CLOUDSC_COLSUM2);
+        if (sinksum > mm2) {
+          const T ratio = CLOUDSC_DIV(mm2, sinksum);
+          CLOUDSC_SCALE_LO(a02); CLOUDSC_SCALE_LO(a12); CLOUDSC_SCALE_D(d2); CLOUDSC_SCALE_HI(a23); CLOUDSC_SCALE_HI(a24);
+        }
+        sinksum = zero - (CLOUDSC_COLSUM3);
+        if (sinksum > mm3) {
+          const T ratio = CLOUDSC_DIV(mm3, sinksum);
+          CLOUDSC_SCALE_LO(a03); CLOUDSC_SCALE_LO(a23); CLOUDSC_SCALE_D(d3); CLOUDSC_SCALE_HI(a34);
+        }
+        sinksum = zero - (CLOUDSC_COLSUM4);
+        if (sinksum > mm4) {
+          const T ratio = CLOUDSC_DIV(mm4, sinksum);
+          CLOUDSC_SCALE_LO(a04); CLOUDSC_SCALE_LO(a14); CLOUDSC_SCALE_LO(a24); CLOUDSC_SCALE_LO(a34);
+        }
+        cs0 = CLOUDSC_COLSUM0; cs1 = CLOUDSC_COLSUM1; cs2 = CLOUDSC_COLSUM2; cs3 = CLOUDSC_COLSUM3; cs4 = CLOUDSC_COLSUM4;
+      }
+#undef CLOUDSC_COLSUM0
+#undef CLOUDSC_COLSUM1
+#undef CLOUDSC_COLSUM2
+#undef CLOUDSC_COLSUM3
+#undef CLOUDSC_COLSUM4
+#undef CLOUDSC_SCALE_LO
+#undef CLOUDSC_SCALE_HI
+#undef CLOUDSC_SCALE_D
+}
+
+/*
+ * 5.2.2 implicit solve, cloudsc_c.c:2294-2412.  RHS :2326-2337 = qx + the limited explicit sums.  LHS: diag
+ * den_m = 1 + fallsink_m + sum_n qb[m][n], off-diagonals -qb[m][n]; the only non-zero qb are (l,l) (i,i) (l,s) (i,s),
+ * i.e. the transposed system is lower triangular with the single sub-diagonal row "snow <- liquid, ice".  The
+ * reference's non-pivoting LU then produces exactly two multipliers, -qb03/den0 and -qb13/den1, leaves every diagonal
+ * unchanged, and the back-substitution is a plain divide per species.  Then the clipping of :2402-2412.
+ */
+template <typename T>
+CLOUDSC_FN void implicit_solve(const CloudscConst<T> &c, const T (&qx)[4], const T qv, const T cs0, const T cs1, const T cs2,
+                               const T cs3, const T cs4, const T qb00, const T qb11, const T qb03, const T qb13,
+                               const T fallsink1, const T fallsink2, const T fallsink3, T (&qxn)[5]) {
+  const T zero = T(0.0), one = T(1.0);
+      qxn[0] = qx[0] + cs0;
+      qxn[1] = qx[1] + cs1;
+      qxn[2] = qx[2] + cs2;
+      qxn[3] = qx[3] + cs3;
+      qxn[4] = qv + cs4;
+      {
+        const T den0 = ((one + zero) + qb00) + qb03;
+        const T den1 = ((one + fallsink1) + qb11) + qb13;
+        const T den2 = one + fallsink2;
+        const T den3 = one + fallsink3;
+        const T r_den0 = CLOUDSC_RCP(den0), r_den1 = CLOUDSC_RCP(den1);
+        (void)r_den0; (void)r_den1;
+        const T l03 = CLOUDSC_DIVR(-qb03, den0, r_den0);
+        const T l13 = CLOUDSC_DIVR(-qb13, den1, r_den1);
+        qxn[3] = qxn[3] - l03 * qxn[0];
+        qxn[3] = qxn[3] - l13 * qxn[1];
+        qxn[3] = CLOUDSC_DIV(qxn[3], den3);
+        qxn[2] = CLOUDSC_DIV(qxn[2], den2);
+        qxn[1] = CLOUDSC_DIVR(qxn[1], den1, r_den1);
+        qxn[0] = CLOUDSC_DIVR(qxn[0], den0, r_den0);
+      }
+      /* clip small/negative values into vapour, :2402-2412 -- as selects: the four tests are independent
+       * and qxn[v] + 0 == qxn[v] where the reference adds nothing */
+      {
+        const bool c0 = qxn[0] < c.zepsec, c1 = qxn[1] < c.zepsec, c2 = qxn[2] < c.zepsec, c3 = qxn[3] < c.zepsec;
+        qxn[4] = (((qxn[4] + (c0 ? qxn[0] : zero)) + (c1 ? qxn[1] : zero)) + (c2 ? qxn[2] : zero)) + (c3 ? qxn[3] : zero);
+        qxn[0] = c0 ? zero : qxn[0]; qxn[1] = c1 ? zero : qxn[1]; qxn[2] = c2 ? zero : qxn[2]; qxn[3] = c3 ? zero : qxn[3];
+      }
+}
+
+/*
  * The column sweep.  IO must provide
  *   template<int S> T ld(int k) const;        input slot S at level k (0-based), read while level k
  *                                             is being processed
@@ -1122,102 +1232,14 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T da = anew - aorig_e;
       s.anewm1 = anew;
 
-      /* ================= 5.2 sink limiter, :2233-2286 ===================================== */
-      /* (the first pass :2207-2227 is overwritten before use).  zratio = zmm/max(zsinksum,zmm) is
-       * exactly 1 unless the sinks of species m exceed its content, and scaling by 1 is the
-       * identity -- so the divide and the scaling only run in that case. */
-      /* column sums sum_n zsolqa[n][m], n = 0..4 in the reference's order (:2239, :2330) */
-#define CLOUDSC_COLSUM0 ((((zero + d0) - a01) - a02) - a03) - a04
-#define CLOUDSC_COLSUM1 (((zero + a01) + d1) - a12) - a14
-#define CLOUDSC_COLSUM2 ((((zero + a02) + a12) + d2) - a23) - a24
-#define CLOUDSC_COLSUM3 (((zero + a03) + a23) + d3) - a34
-#define CLOUDSC_COLSUM4 (((zero + a04) + a14) + a24) + a34
-      /* "if zsolqa[n][m] < 0 scale the pair": a_nm itself for n < m, a_mn > 0 for n > m; a negative
-       * diagonal is scaled twice (n == m hits both statements of :2281-2282) */
-#define CLOUDSC_SCALE_LO(a) if ((a) < zero) (a) = (a) * ratio
-#define CLOUDSC_SCALE_HI(a) if ((a) > zero) (a) = (a) * ratio
-#define CLOUDSC_SCALE_D(d) if ((d) < zero) (d) = ((d) * ratio) * ratio
-      /* The five species are limited one after the other (a scaled pair feeds the later column sums),
-       * but when no column exceeds its content -- the common case -- nothing is scaled at all and the
-       * five unscaled sums are also the explicit sums of :2330.  So: all five sums and tests up front
-       * (independent chains), and the sequential pass only if one of them fires; by induction over m
-       * the pass cannot fire unless one of the up-front tests does. */
-      T cs0 = CLOUDSC_COLSUM0, cs1 = CLOUDSC_COLSUM1, cs2 = CLOUDSC_COLSUM2, cs3 = CLOUDSC_COLSUM3, cs4 = CLOUDSC_COLSUM4;
-      const T mm0 = mx(qx[0], c.zepsec), mm1 = mx(qx[1], c.zepsec), mm2 = mx(qx[2], c.zepsec), mm3 = mx(qx[3], c.zepsec),
-              mm4 = mx(qv, c.zepsec);
-      if (CLOUDSC_RARE((zero - cs0 > mm0) | (zero - cs1 > mm1) | (zero - cs2 > mm2) | (zero - cs3 > mm3) | (zero - cs4 > mm4))) {
-        T sinksum = zero - cs0;
-        if (sinksum > mm0) {
-          const T ratio = CLOUDSC_DIV(mm0, sinksum);
-          CLOUDSC_SCALE_D(d0); CLOUDSC_SCALE_HI(a01); CLOUDSC_SCALE_HI(a02); CLOUDSC_SCALE_HI(a03); CLOUDSC_SCALE_HI(a04);
-        }
-        sinksum = zero - (CLOUDSC_COLSUM1);
-        if (sinksum > mm1) {
-          const T ratio = CLOUDSC_DIV(mm1, sinksum);
-          CLOUDSC_SCALE_LO(a01); CLOUDSC_SCALE_D(d1); CLOUDSC_SCALE_HI(a12); CLOUDSC_SCALE_HI(a14);
-        }
-        sinksum = zero - (CLOUDSC_COLSUM2);
-        if (sinksum > mm2) {
-          const T ratio = CLOUDSC_DIV(mm2, sinksum);
-          CLOUDSC_SCALE_LO(a02); CLOUDSC_SCALE_LO(a12); CLOUDSC_SCALE_D(d2); CLOUDSC_SCALE_HI(a23); CLOUDSC_SCALE_HI(a24);
-        }
-        sinksum = zero - (CLOUDSC_COLSUM3);
-        if (sinksum > mm3) {
-          const T ratio = CLOUDSC_DIV(mm3, sinksum);
-          CLOUDSC_SCALE_LO(a03); CLOUDSC_SCALE_LO(a23); CLOUDSC_SCALE_D(d3); CLOUDSC_SCALE_HI(a34);
-        }
-        sinksum = zero - (CLOUDSC_COLSUM4);
-        if (sinksum > mm4) {
-          const T ratio = CLOUDSC_DIV(mm4, sinksum);
-          CLOUDSC_SCALE_LO(a04); CLOUDSC_SCALE_LO(a14); CLOUDSC_SCALE_LO(a24); CLOUDSC_SCALE_LO(a34);
-        }
-        cs0 = CLOUDSC_COLSUM0; cs1 = CLOUDSC_COLSUM1; cs2 = CLOUDSC_COLSUM2; cs3 = CLOUDSC_COLSUM3; cs4 = CLOUDSC_COLSUM4;
-      }
-
-      /* ================= 5.2.2 implicit solve, :2294-2397 ================================= */
-      /*
-       * RHS :2326-2337.  LHS: diag den_m = 1 + fallsink_m + sum_n qb[m][n], off-diagonals -qb[m][n];
-       * the only non-zero qb are (l,l) (i,i) (l,s) (i,s), i.e. the transposed system is lower
-       * triangular with the single sub-diagonal row "snow <- liquid, ice".  The reference's
-       * non-pivoting LU then produces exactly two multipliers, -qb03/den0 and -qb13/den1, leaves
-       * every diagonal unchanged, and the back-substitution is a plain divide per species.
-       */
+      /* ================= 5.2 sink limiter (:2233-2286) and 5.2.2 implicit solve (:2294-2412) ===== */
+      /* (functions above: sink_limiter(), implicit_solve(); unit-tested against a dense restatement of the reference's
+       * statements in tests/test_unit_processes.py) */
       T qxn[5];
-      qxn[0] = qx[0] + cs0;
-      qxn[1] = qx[1] + cs1;
-      qxn[2] = qx[2] + cs2;
-      qxn[3] = qx[3] + cs3;
-      qxn[4] = qv + cs4;
-#undef CLOUDSC_COLSUM0
-#undef CLOUDSC_COLSUM1
-#undef CLOUDSC_COLSUM2
-#undef CLOUDSC_COLSUM3
-#undef CLOUDSC_COLSUM4
-#undef CLOUDSC_SCALE_LO
-#undef CLOUDSC_SCALE_HI
-#undef CLOUDSC_SCALE_D
       {
-        const T den0 = ((one + zero) + qb00) + qb03;
-        const T den1 = ((one + fallsink1) + qb11) + qb13;
-        const T den2 = one + fallsink2;
-        const T den3 = one + fallsink3;
-        const T r_den0 = CLOUDSC_RCP(den0), r_den1 = CLOUDSC_RCP(den1);
-        (void)r_den0; (void)r_den1;
-        const T l03 = CLOUDSC_DIVR(-qb03, den0, r_den0);
-        const T l13 = CLOUDSC_DIVR(-qb13, den1, r_den1);
-        qxn[3] = qxn[3] - l03 * qxn[0];
-        qxn[3] = qxn[3] - l13 * qxn[1];
-        qxn[3] = CLOUDSC_DIV(qxn[3], den3);
-        qxn[2] = CLOUDSC_DIV(qxn[2], den2);
-        qxn[1] = CLOUDSC_DIVR(qxn[1], den1, r_den1);
-        qxn[0] = CLOUDSC_DIVR(qxn[0], den0, r_den0);
-      }
-      /* clip small/negative values into vapour, :2402-2412 -- as selects: the four tests are independent
-       * and qxn[v] + 0 == qxn[v] where the reference adds nothing */
-      {
-        const bool c0 = qxn[0] < c.zepsec, c1 = qxn[1] < c.zepsec, c2 = qxn[2] < c.zepsec, c3 = qxn[3] < c.zepsec;
-        qxn[4] = (((qxn[4] + (c0 ? qxn[0] : zero)) + (c1 ? qxn[1] : zero)) + (c2 ? qxn[2] : zero)) + (c3 ? qxn[3] : zero);
-        qxn[0] = c0 ? zero : qxn[0]; qxn[1] = c1 ? zero : qxn[1]; qxn[2] = c2 ? zero : qxn[2]; qxn[3] = c3 ? zero : qxn[3];
+        T cs0, cs1, cs2, cs3, cs4;
+        sink_limiter<T>(c, a01, a02, a03, a04, a12, a14, a23, a24, a34, d0, d1, d2, d3, qx, qv, cs0, cs1, cs2, cs3, cs4);
+        implicit_solve<T>(c, qx, qv, cs0, cs1, cs2, cs3, cs4, qb00, qb11, qb03, qb13, fallsink1, fallsink2, fallsink3, qxn);
       }
       /* variables needed for next level, :2417-2423 */
       s.qlnm1 = qxn[0]; s.qinm1 = qxn[1];

@@ -36,7 +36,7 @@ def built():
     import subprocess
     from dwarf_p_cloudsc_b200 import build
     build.build_all()
-    targets = ["emul"]
+    targets = ["emul", "unit"]
     if os.path.exists(os.path.join(ROOT, "oracle", "cloudsc_oracle.c")):
         targets.append("port")
     if os.path.exists("/root/reference/src/cloudsc_c/cloudsc/cloudsc_c.c"):

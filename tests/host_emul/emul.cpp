@@ -192,6 +192,34 @@ int cloudsc_emul_blocks_ranged_f64(const struct TECLDP *p, const struct cloudsc_
                                    int ngptot, int nproma, int klev, double ptsphy, int cut1, int cut2) {
   return run_ranged<double>(p, k, fields, ngptot, nproma, klev, ptsphy, cut1, cut2);
 }
+/* ---- per-process entry points (tests/test_unit_processes.py): the device code's sink limiter, implicit solve and
+ * Newton step, called on their own.  a[13] = a01 a02 a03 a04 a12 a14 a23 a24 a34 d0 d1 d2 d3 (cloudsc_column.cuh). */
+void cloudsc_emul_unit_limiter(double a[13], const double qx5[5], double cs[5]) {
+  CloudscConst<double> c;
+  memset(&c, 0, sizeof(c));
+  c.zepsec = 1.0e-14;
+  const double qx[4] = {qx5[0], qx5[1], qx5[2], qx5[3]};
+  sink_limiter<double>(c, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], qx, qx5[4],
+                       cs[0], cs[1], cs[2], cs[3], cs[4]);
+}
+void cloudsc_emul_unit_solve(const double qx5[5], const double cs[5], const double qb[4], const double fallsink[3], double qxn_out[5]) {
+  CloudscConst<double> c;
+  memset(&c, 0, sizeof(c));
+  c.zepsec = 1.0e-14;
+  const double qx[4] = {qx5[0], qx5[1], qx5[2], qx5[3]};
+  double qxn[5];
+  implicit_solve<double>(c, qx, qx5[4], cs[0], cs[1], cs[2], cs[3], cs[4], qb[0], qb[1], qb[2], qb[3], fallsink[0], fallsink[1],
+                         fallsink[2], qxn);
+  for (int i = 0; i < 5; i++) qxn_out[i] = qxn[i];
+}
+int cloudsc_emul_unit_satadj(const struct TECLDP *p, const struct cloudsc_consts *k, double qp, double *tn, double *qsm) {
+  if (check_params(p)) return CLOUDSC_B200_EPARAMS;
+  CloudscConst<double> c;
+  fill_consts<double>(p, k, &c);
+  exp2_tab_init();
+  satadj_step<double>(c, qp, *tn, *qsm);
+  return 0;
+}
 int cloudsc_emul_blocks_f32(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
                             int ngptot, int nproma, int klev, double ptsphy) {
   return run<float>(p, k, fields, ngptot, nproma, klev, ptsphy);

@@ -247,3 +247,25 @@ def test_c_h5lite_rejects_a_truncated_or_inconsistent_file(hostlib, tmp_path):
     assert hostlib.h5lite_read_double(f, b"A", big.ctypes.data_as(_dp), 1400) == -1
     assert b"exceeds its storage" in hostlib.h5lite_error()
     hostlib.h5lite_close(f)
+
+
+@pytest.mark.parametrize("args", [("2", "100", "16"), ("1", "300", "64")])
+def test_reference_executable_runs_on_our_loader(built, args):
+    """oracle/_ref/dwarf-cloudsc-c = the reference's OWN dwarf-cloudsc-c (dwarf_cloudsc.c, cloudsc_driver.c, cloudsc_c.c,
+    cloudsc_validate.c, yo*_c.c, all unmodified) with host/load_state.c + host/h5lite.c standing in for load_state.c +
+    libhdf5.  Its own error table against reference.h5 must be clean: this pins the loader end to end (input.h5 ->
+    expand_* -> the reference kernel -> load_reference) and is the executable behind BASELINE configs[0]."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "dwarf-cloudsc-c")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dwarf-cloudsc-c not built (needs /root/reference or a prebuilt copy)")
+    env = dict(os.environ, OMP_NUM_THREADS=args[0], OMP_STACKSIZE="256M")
+    r = subprocess.run([exe, *args], cwd=GOLDEN, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f"NUMOMP={args[0]}, NGPTOT={args[1]}, NPROMA={args[2]}" in r.stdout
+    rows = [l.split() for l in r.stdout.splitlines() if len(l.split()) >= 7 and l.split()[1][:2] == "2D"]
+    assert len(rows) == 21, r.stdout
+    for row in rows:
+        vmin, vmax, maxerr, avgerr, relerr = map(float, row[2:7])
+        assert np.isfinite([vmin, vmax, maxerr, avgerr, relerr]).all(), row
+        assert maxerr <= 1e-12 * max(abs(vmin), abs(vmax), 1e-300) or maxerr == 0.0, row     # C kernel vs the Fortran-made file: <= 3e-13
+    assert "TOTAL" in r.stdout
