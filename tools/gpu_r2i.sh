@@ -1,14 +1,7 @@
 #!/bin/bash
-# Round 2: full GPU suite on the refactored tree, both bench arms, BASELINE configs[0] on the box's host cores,
-# configs[3]/[4] sweeps.
+# configs[0] on the box host + configs[3]/[4] sweeps (second half of tools/gpu_r2h.sh)
 set -x
 mkdir -p gpurun_out
-timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r2h.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke_r2h.log
-timeout -s KILL 1500 python -m pytest tests -m gpu -q --durations=8 > gpurun_out/pytest_gpu_r2h.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_r2h.log
-tail -25 gpurun_out/pytest_gpu_r2h.log
-timeout -s KILL 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_r2h.json 2> gpurun_out/bench_ref_r2h.err
-timeout -s KILL 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2h.json 2> gpurun_out/bench_r2h.err; echo "bench rc=$?" >> gpurun_out/bench_r2h.err
-cat gpurun_out/bench_r2h.json | cut -c1-600; tail -4 gpurun_out/bench_r2h.err
 (
   set +x
   NC=$(nproc)
