@@ -487,16 +487,17 @@ int cloudsc_b200_destroy(cloudsc_b200_state *st) {
 /*
  * How step() walks the tiles of a launch ("persistent kernel"):
  *   mode 0  one one-warp CTA per 32-column tile, every tile swept top to bottom in one go
+ *   mode 2  streaming: 12 persistent warps per SM taking tiles from a queue, the input ring kept full across tiles
  *   mode 1  persistent: 12 warps per SM, each running its tiles in two pieces (levels [0, ksplit) and [ksplit, klev))
  *           and choosing the next piece so that about target_b of the SM's warps are in a lower piece at any time
  * ksplit <= 0 -> 3*klev/5; target_b <= 0 -> 7 of 12.  Results are bit-identical in every mode.
  */
 int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b) {
   if (!st) return fail(CLOUDSC_B200_EARG, "set_schedule: NULL state");
-  if (mode != 0 && mode != 1) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
+  if (mode < 0 || mode > 2) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
   if (ksplit >= st->klev) return fail(CLOUDSC_B200_EARG, "set_schedule: ksplit must be below klev");
   if (int rc = state_on_current_device(st, "set_schedule")) return rc;
-  if (mode == 1 && st->has_tm && !st->sched.carry) {
+  if (mode >= 1 && st->has_tm && !st->sched.carry) {
     const int ntiles = (st->nblocks * st->nproma + 31) / 32;
     CU(cudaMalloc(&st->sched.carry, persist_carry_bytes(ntiles, st->precision)));
     CU(cudaMalloc((void **)&st->sched.sm_b, 1024 * sizeof(int)));
@@ -504,6 +505,7 @@ int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int 
     st->sched.carry_tiles = ntiles;
   }
   st->sched_mode = mode;
+  st->sched.mode = mode;
   st->sched.ksplit = ksplit;
   st->sched.target_b = target_b;
   return 0;
@@ -563,7 +565,7 @@ int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, in
   if (end > st->ngptot) end = st->ngptot;
   LaunchGeom g{first_block * st->nproma, (int)end, st->nproma, st->klev};
   const int variant = g_variant.load();
-  if (st->has_tm && variant == VARIANT_AUTO && st->sched_mode == 1)
+  if (st->has_tm && variant == VARIANT_AUTO && st->sched_mode >= 1)
     CU(launch_sweep_persist(ft, st->tm, g, ptsphy, st->precision, st->sched, (cudaStream_t)stream));
   else if (st->has_tm && variant == VARIANT_AUTO)
     CU(launch_sweep_tmap(ft, st->tm, g, ptsphy, st->precision, (cudaStream_t)stream));

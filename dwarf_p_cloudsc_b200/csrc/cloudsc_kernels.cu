@@ -371,13 +371,17 @@ struct TmapIO {
   /* RANGED only */
   int kb, ke, kofs;
   T *carry;                           /* this tile's [kCarryVals][32] block + lane */
+  int n_ibl, n_jl0;                   /* streaming schedule: the tile this warp sweeps next (n_ibl < 0: none); its levels 0
+                                         and 1 are requested during the last two levels of this tile, so that the ring never
+                                         drains between tiles */
 
   __device__ __forceinline__ int it_of(int level) const { return RANGED ? level + kofs : level; }
   __device__ __forceinline__ int k_begin() const { return kb; }
   __device__ __forceinline__ int k_end() const { return ke; }
 
-  __device__ __forceinline__ void issue(int level) {   /* one elected lane */
-    const unsigned st = (unsigned)it_of(level) & 1u;
+  __device__ __forceinline__ void issue(int level) { issue_tile(level, it_of(level), ibl, jl0); }   /* one elected lane */
+  __device__ __forceinline__ void issue_tile(int level, int it, int ibl, int jl0) {
+    const unsigned st = (unsigned)it & 1u;
     const unsigned bar = bar0 + 8u * st;
     const unsigned dst = smem0 + st * (unsigned)kStage;
     if (level < ktop1) {
@@ -417,6 +421,9 @@ struct TmapIO {
     __syncwarp();               /* every lane is done reading stage k&1 */
     if (k + 2 < (RANGED ? ke : klev)) {
       if (elect_one()) issue(k + 2);
+      __syncwarp();
+    } else if (RANGED && n_ibl >= 0) {   /* (only with kb == 0, ke == klev: the streaming schedule) */
+      if (elect_one()) issue_tile(k + 2 - ke, it_of(k + 2), n_ibl, n_jl0);
       __syncwarp();
     }
     cL += (unsigned)stride; cH1 += (unsigned)stride; cC += (unsigned)stride;
@@ -480,7 +487,7 @@ cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant_
         reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
         bH + jl, (long long)ibl * g.nproma + jl,
         (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma),
-        ccol + (int)threadIdx.x < g.col_end, 0, g.klev, 0, nullptr};
+        ccol + (int)threadIdx.x < g.col_end, 0, g.klev, 0, nullptr, -1, 0};
   if (threadIdx.x == 0) {
     mbar_init(io.bar0, 1);
     mbar_init(io.bar0 + 8, 1);
@@ -566,7 +573,7 @@ cloudsc_sweep_persist(const __grid_constant__ FieldTable ft, const __grid_consta
           bH + jl, (long long)ibl * g.nproma + jl,
           (unsigned)(bL + jl) + rows, (unsigned)(bH + jl + g.nproma) + rows, (unsigned)(bL * 5 + jl) + rows, (unsigned)(g.klev * g.nproma),
           ccol + (int)threadIdx.x < g.col_end, kb, ke, staged - kb,
-          static_cast<T *>(plan.carry) + (size_t)tile * (kCarryVals * 32) + threadIdx.x};
+          static_cast<T *>(plan.carry) + (size_t)tile * (kCarryVals * 32) + threadIdx.x, -1, 0};
     if (elect_one()) {
       io.issue(kb);
       if (kb + 1 < ke) io.issue(kb + 1);
@@ -577,6 +584,64 @@ cloudsc_sweep_persist(const __grid_constant__ FieldTable ft, const __grid_consta
     staged += ke - kb;
     if (do_b) { ++b_done; if (threadIdx.x == 0) atomicSub(sm_b, 1); }
     else ++a_done;
+  }
+}
+
+/* ---- streaming kernel: persistent warps, tiles from a queue, the input ring never drains --------------------------- */
+/*
+ * Schedule mode 2.  The grid is the resident set; every warp takes its next 32-column tile from a global counter (so the
+ * tiles go to whichever warp is free, as with one CTA per tile) and sweeps it top to bottom in one piece, but requests the
+ * first two levels of the NEXT tile during the last two levels of the current one: no CTA launch, no barrier set-up and no
+ * empty input ring between two tiles of a warp.
+ */
+template <typename T>
+__global__ void __launch_bounds__(32, warps_per_sm<T>())
+cloudsc_sweep_stream(const __grid_constant__ FieldTable ft, const __grid_constant__ TensorMaps tm, const LaunchGeom g,
+                     const __grid_constant__ StepConst<T> sc, const int ntiles, int *const queue) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using IO = TmapIO<T, true>;
+  const unsigned bar0 = smem_u32(smem_raw + 2 * IO::kStage);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  /* the first gridDim.x tiles are dealt by block index, the rest through the queue (which starts at gridDim.x) */
+  int tile = (int)blockIdx.x;
+  if (tile >= ntiles) return;
+  int staged = 0;
+  bool primed = false;
+  while (tile < ntiles) {
+    int next = 0;
+    if (threadIdx.x == 0) next = atomicAdd(queue, 1);
+    next = __shfl_sync(0xffffffffu, next, 0);
+    const int ccol = g.col_begin + tile * IO::kCols;
+    const int ibl = ccol / g.nproma;
+    const int jl0 = ccol - ibl * g.nproma;
+    const int jl = jl0 + (int)threadIdx.x;
+    const int ncol = g.col_begin + next * IO::kCols;
+    const int n_ibl = next < ntiles ? ncol / g.nproma : -1;
+    const int n_jl0 = next < ntiles ? ncol - n_ibl * g.nproma : 0;
+    const long long bL = (long long)ibl * g.klev * g.nproma, bH = (long long)ibl * (g.klev + 1) * g.nproma;
+    IO io{ft, tm, ibl, jl0, g.nproma, g.klev, dev_consts<T>().ncldtop - 2,
+          smem_u32(smem_raw), bar0,
+          reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
+          bH + jl, (long long)ibl * g.nproma + jl,
+          (unsigned)(bL + jl), (unsigned)(bH + jl + g.nproma), (unsigned)(bL * 5 + jl), (unsigned)(g.klev * g.nproma),
+          ccol + (int)threadIdx.x < g.col_end, 0, g.klev, staged, nullptr, n_ibl, n_jl0};
+    if (!primed) {
+      if (elect_one()) {
+        io.issue(0);
+        io.issue(1);
+      }
+      __syncwarp();
+      primed = true;
+    }
+    cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+    __syncwarp();
+    staged += g.klev;
+    tile = next;
   }
 }
 
@@ -942,8 +1007,26 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     if (e != cudaSuccess) return e;
   }
   const int resident = sms[dev & 63] * per_sm[dev & 63][pi];
+  static int resident_h[64];                          /* stable host storage for the asynchronous queue reset */
+  resident_h[dev & 63] = resident;
   /* fewer tiles than two full rounds of the resident set: nothing to interleave */
   if (resident <= 0 || ntiles < 2 * resident) return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
+  if (ps.mode == 2) {
+    const void *sfn = (const void *)cloudsc_sweep_stream<T>;
+    e = cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int *queue = ps.sm_b + 512;                       /* (the per-SM counters of mode 1 use the first half) */
+    e = cudaMemcpyAsync(queue, &resident_h[dev & 63], sizeof(int), cudaMemcpyHostToDevice, stream);   /* queue starts at the grid size */
+    if (e != cudaSuccess) return e;
+    StepConst<T> sc2;
+    fill_step<T>(host_consts<T>(dev), ptsphy, &sc2);
+    int nt = ntiles;
+    void *sargs[] = {(void *)&ft, (void *)&tm, (void *)&g, (void *)&sc2, (void *)&nt, (void *)&queue};
+    ++g_launches[KERNEL_TMAP];
+    return cudaLaunchKernel(sfn, dim3(resident), dim3(32), sargs, smem, stream);
+  }
   int ksplit = ps.ksplit > 0 ? ps.ksplit : (3 * g.klev) / 5;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > g.klev - 1) ksplit = g.klev - 1;

@@ -67,6 +67,7 @@ cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const 
 /* persistent variant of the tensor-map kernel (cloudsc_kernels.cu, "persistent kernel"); falls back to launch_sweep_tmap
  * for launches with fewer than two rounds of tiles per resident warp.  ksplit / target_b <= 0: defaults. */
 struct PersistSchedule {
+  int mode;         /* 1: interleaved upper / lower pieces (cloudsc_sweep_persist); 2: streaming tile queue (cloudsc_sweep_stream) */
   int ksplit, target_b;
   void *carry;      /* persist_carry_bytes(carry_tiles, precision) bytes of device scratch */
   int carry_tiles;

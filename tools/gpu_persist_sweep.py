@@ -6,8 +6,9 @@ import numpy as np
 import torch
 from dwarf_p_cloudsc_b200 import api, params, state
 
-ngptot = int(sys.argv[1]) if len(sys.argv) > 1 else 163840
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+ngptot = int(_pos[0]) if len(_pos) > 0 else 163840
+steps = int(_pos[1]) if len(_pos) > 1 else 20
 nproma = 128
 cols, scalars, _, klev = state.load_input()
 p, k = params.params_from_scalars(scalars)
@@ -38,7 +39,9 @@ def run(mode, ks, tb):
 
 base_ms, base_min, base = run(0, 0, 0)
 print(f"mode 0 (one CTA per tile)          : {base_ms:.4f} ms (min {base_min:.4f})", flush=True)
-settings = [(1, 0, 0)] + [(1, ks, tb) for ks in (82, 70, 90, 60) for tb in (4, 6, 7, 8, 12, 1)]
+settings = [(2, 0, 0), (1, 1, 12), (1, 136, 12), (1, 82, 12), (1, 90, 6), (2, 0, 0)]
+if "--full" in sys.argv:
+    settings = [(1, 0, 0)] + [(1, ks, tb) for ks in (82, 70, 90, 60) for tb in (4, 6, 7, 8, 12, 1)]
 for mode, ks, tb in settings:
     ms, mn, G = run(mode, ks, tb)
     same = all(np.array_equal(G[n], base[n]) for n in outs)
