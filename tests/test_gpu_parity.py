@@ -816,3 +816,33 @@ def test_c_driver_power_sampling(built):
     r = subprocess.run([exe, "1", "1000", "100"], cwd=os.path.join(root, "tests", "golden"), capture_output=True, text=True, timeout=600,
                        env={k: v for k, v in os.environ.items() if k != "EC_PMON"})
     assert r.returncode == 0 and "Power usage" not in r.stdout
+
+
+@pytest.mark.parametrize("flags", [0, 1, 2])
+def test_library_host_buffers(built, oracle, input_data, flags):
+    """cloudsc_b200_host_alloc_ex: plain page-locked memory, write-combined (upload side), and 2 MB pages first-touched by
+    the caller + cudaHostRegister -- run_host on arrays living in each kind gives the oracle's answer; host_free takes all."""
+    from dwarf_p_cloudsc_b200 import api, params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    ngptot, nproma = 1500, 128
+    F = state.blocked_fields(cols, ngptot, nproma, klev)
+    R = {n: a.copy() for n, a in F.items()}
+    oracle.run(R, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 0)
+    api.set_params(p, k)
+    bufs, H = [], {}
+    try:
+        for f in params.FIELDS:
+            if f.name not in F:
+                continue
+            # write-combined memory is for buffers the CPU only writes: inputs only
+            hb = api.HostBuffer(F[f.name].shape, F[f.name].dtype, flags if (flags != 1 or f.use == "R") else 0)
+            hb.array[...] = F[f.name]
+            bufs.append(hb)
+            H[f.name] = hb.array
+        api.run_host(H, ngptot, nproma, klev, scalars["PTSPHY"], chunk_blocks=3, nstreams=3)
+        _compare({n: np.array(a) for n, a in H.items()}, R, ngptot)
+    finally:
+        H.clear()
+        for hb in bufs:
+            hb.free()
