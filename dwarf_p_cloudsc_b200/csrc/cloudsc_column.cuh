@@ -482,6 +482,41 @@ CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
 }
 
 /*
+ * The part of 3.7 (ice deposition, Rotstayn; cloudsc_c.c:1398-1431) that depends on the level's inputs only: the new ice
+ * content zinew a pre-existing ice amount zice0 grows to, and zinfactor.  Everything downstream of it (zdepos and its
+ * limits) depends on the first-guess liquid of this level.
+ */
+template <typename T>
+CLOUDSC_FN void deposition_prep(const CloudscConst<T> &c, const T ptsphy, const T t, const T pap, const T rho, const T r_rho,
+                                const T r_t, const T e_ice, const T fokoop, const T icecld, T &inew, T &ice0, T &infactor) {
+  const T one = T(1.0);
+  (void)r_rho; (void)r_t;
+  const T vpice = CLOUDSC_DIVR((c.r2es * e_ice) * c.rv, c.rd, c.r_rd);
+  const T vpliq = vpice * fokoop;
+  const T icenuclei = T(1000.0) * CLOUDSC_EXP_COLD(CLOUDSC_DIV(c.p1296 * (vpliq - vpice), vpliq) - c.p0639);
+#if CLOUDSC_STRICT
+  const T add = (c.rlstt * (c.rlstt / (c.rv * t) - one)) / (c.p0024 * t);
+  const T bdd = ((c.rv * t) * pap) / (c.p221 * vpice);
+  const T cvds = ((c.p78 * pw(icenuclei / rho, c.p0666)) * (vpliq - vpice)) / ((c.p887 * (add + bdd)) * vpice);
+  ice0 = mx(icecld, (icenuclei * c.riceinit) / rho);
+#else
+  const T add = (c.rlstt * ((c.rlstt * c.r_rv) * r_t - one)) * (c.r_p0024 * r_t);
+  const T bdd = ((c.rv * t) * pap) * rcp_fast(c.p221 * vpice);
+  const T cvds = ((c.p78 * CLOUDSC_POW(icenuclei * r_rho, c.p0666)) * (vpliq - vpice)) * rcp_fast((c.p887 * (add + bdd)) * vpice);
+  ice0 = mx(icecld, (icenuclei * c.riceinit) * r_rho);
+#endif
+  inew = CLOUDSC_POW15((c.p0666 * cvds) * ptsphy + CLOUDSC_POW(ice0, c.p0666));
+  infactor = mn(CLOUDSC_DIVR(icenuclei, T(15000.0), c.r_15000), one);
+}
+
+/* CLOUDSC_DEPOS_EARLY (experiment): evaluate deposition_prep() next to the Newton steps of 3.4 -- both are long dependent
+ * chains on the level's inputs only, in one basic block they overlap -- where supercooled liquid is already there at the
+ * start of the level; the deposition block falls back to evaluating it itself where liquid only appears during the level. */
+#ifndef CLOUDSC_DEPOS_EARLY
+#define CLOUDSC_DEPOS_EARLY 0
+#endif
+
+/*
  * 5.2 sink limiter, cloudsc_c.c:2233-2286, on the antisymmetric representation of ZSOLQA (a_xy = zsolqa[x][y] for
  * x < y, diagonal d_m; species 0=l 1=i 2=r 3=s 4=v; the pair (i,s) and d_v are never written by any process).
  * (The first pass :2207-2227 is overwritten before use.)  zratio = zmm/max(zsinksum,zmm) is exactly 1 unless the sinks
@@ -774,6 +809,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 #if CLOUDSC_STRICT
       const T rho = pap / (c.rd * t);
       const T r_rho = one / rho;
+      const T r_t = one / t;   /* (unused in strict mode: deposition_prep() divides) */
 #else
       const T r_t = rcp_fast(t);
       const T rho = (pap * c.r_rd) * r_t;
@@ -834,6 +870,9 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* (evaluated here, ahead of 3.1-3.4: it is a pure function of this level's inputs, and next to the
        * saturation block its two Newton steps overlap with that block's exp/reciprocal chains) */
       T dqs = zero;
+      T dep_inew = zero, dep_ice0 = zero, dep_infactor = zero;
+      bool dep_ready = false;
+      (void)dep_ready;
       if (need_dqs) {
         const T dtdp = CLOUDSC_DIVR(sc.zrdcp * t, pap, r_pap);
         const T dpmxdt = dp * zqtmst;
@@ -846,6 +885,12 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         T tn = t + dtforc;
         tn = mx(tn, T(160.0));
         T qsm = qsmix;
+#if CLOUDSC_DEPOS_EARLY && !CLOUDSC_STRICT
+        if (qx[0] > c.rlmin && t < c.rtt) {
+          deposition_prep<T>(c, ptsphy, t, pap, rho, r_rho, r_t, e_ice, fokoop, icecld, dep_inew, dep_ice0, dep_infactor);
+          dep_ready = true;
+        }
+#endif
         satadj_step(c, r_pap, tn, qsm);
         satadj_step(c, r_pap, tn, qsm);
         dqs = qsm - qsmix;
@@ -1004,24 +1049,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 #endif
       park_st<PARK_CLDTOPDIST>(io, s.cldtopdist, s.cldtopdist);
       if (qxfg[0] > c.rlmin && t < c.rtt) {
-        const T vpice = CLOUDSC_DIVR((c.r2es * e_ice) * c.rv, c.rd, c.r_rd);
-        const T vpliq = vpice * fokoop;
-        const T icenuclei = T(1000.0) * CLOUDSC_EXP_COLD(CLOUDSC_DIV(c.p1296 * (vpliq - vpice), vpliq) - c.p0639);
-#if CLOUDSC_STRICT
-        const T add = (c.rlstt * (c.rlstt / (c.rv * t) - one)) / (c.p0024 * t);
-        const T bdd = ((c.rv * t) * pap) / (c.p221 * vpice);
-        const T cvds = ((c.p78 * pw(icenuclei / rho, c.p0666)) * (vpliq - vpice)) / ((c.p887 * (add + bdd)) * vpice);
-        const T ice0 = mx(icecld, (icenuclei * c.riceinit) / rho);
-#else
-        const T add = (c.rlstt * ((c.rlstt * c.r_rv) * r_t - one)) * (c.r_p0024 * r_t);
-        const T bdd = ((c.rv * t) * pap) * rcp_fast(c.p221 * vpice);
-        const T cvds = ((c.p78 * CLOUDSC_POW(icenuclei * r_rho, c.p0666)) * (vpliq - vpice)) * rcp_fast((c.p887 * (add + bdd)) * vpice);
-        const T ice0 = mx(icecld, (icenuclei * c.riceinit) * r_rho);
-#endif
-        const T inew = CLOUDSC_POW15((c.p0666 * cvds) * ptsphy + CLOUDSC_POW(ice0, c.p0666));
+        if (!dep_ready) deposition_prep<T>(c, ptsphy, t, pap, rho, r_rho, r_t, e_ice, fokoop, icecld, dep_inew, dep_ice0, dep_infactor);
+        const T inew = dep_inew, ice0 = dep_ice0, infactor = dep_infactor;
         T depos = mx(a * (inew - ice0), zero);
         depos = mn(depos, qxfg[0]);
-        const T infactor = mn(CLOUDSC_DIVR(icenuclei, T(15000.0), c.r_15000), one);
         depos = depos * mn(infactor + (one - infactor) * (c.rdepliqrefrate + CLOUDSC_DIVR(s.cldtopdist, c.rdepliqrefdepth, c.r_rdepliqrefdepth)), one);
         a01 = a01 + depos;
         qxfg[1] = qxfg[1] + depos; qxfg[0] = qxfg[0] - depos;
