@@ -310,9 +310,121 @@ CLOUDSC_FN double log_fast(double x) {
   const double fe = (double)e;
   return fe * 6.93147180369123816490e-01 + (fe * 1.90821492927058770002e-10 + (lm + lm));
 }
+/*
+ * CLOUDSC_LOG_TABLE: log(x) by table look-up instead of the atanh series.  x = 2^e m, m in [1,2); the top 7 mantissa bits
+ * select c_i = 1 + (i + 1/2)/128 with the pair (invc_i = RN(1/c_i), logc_i = RN(-ln invc_i)); r = fma(m, invc_i, -1) is
+ * exact up to one rounding, |r| <= 2^-8, and log m = logc_i + log1p(r) with the degree-6 Taylor polynomial (truncation
+ * r^7/7 = 2e-18).  Absolute error <= 2.3e-16 max(1, |log x|) -- x^y = exp(y log x) only needs the absolute error.  10 FP64
+ * operations + one 16-byte load instead of 20 + a reciprocal (24 instructions).  On the device the 2 KB table sits in
+ * global memory and is read through the read-only L1 path (the shared memory of the 12 resident one-warp CTAs is full).
+ */
+#ifndef CLOUDSC_LOG_TABLE
+#define CLOUDSC_LOG_TABLE 0
+#endif
+#define CLOUDSC_LOG_TAB_VALUES \
+  0x1.fe01fe01fe020p-1, 0x1.ff00aa2b10ba0p-9, 0x1.fa11caa01fa12p-1, 0x1.7dc475f810a69p-7, \
+  0x1.f6310aca0dbb5p-1, 0x1.3cea44346a584p-6, 0x1.f25f644230ab5p-1, 0x1.b9fc027af919ap-6, \
+  0x1.ee9c7f8458e02p-1, 0x1.1b0d98923d97fp-5, 0x1.eae807aba01ebp-1, 0x1.58a5bafc8e4d3p-5, \
+  0x1.e741aa59750e4p-1, 0x1.95c830ec8e3f2p-5, 0x1.e3a9179dc1a73p-1, 0x1.d276b8adb0b56p-5, \
+  0x1.e01e01e01e01ep-1, 0x1.075983598e471p-4, 0x1.dca01dca01dcap-1, 0x1.253f62f0a1417p-4, \
+  0x1.d92f2231e7f8ap-1, 0x1.42edcbea646eep-4, 0x1.d5cac807572b2p-1, 0x1.60658a93750c4p-4, \
+  0x1.d272ca3fc5b1ap-1, 0x1.7da766d7b12d0p-4, 0x1.cf26e5c44bfc6p-1, 0x1.9ab42462033aep-4, \
+  0x1.cbe6d9601cbe7p-1, 0x1.b78c82bb0eda0p-4, 0x1.c8b265afb8a42p-1, 0x1.d4313d66cb35dp-4, \
+  0x1.c5894d10d4986p-1, 0x1.f0a30c01162a4p-4, 0x1.c26b5392ea01cp-1, 0x1.0671512ca596fp-3, \
+  0x1.bf583ee868d8bp-1, 0x1.14785846742acp-3, 0x1.bc4fd65883e7bp-1, 0x1.2266f190a5acdp-3, \
+  0x1.b951e2b18ff23p-1, 0x1.303d718e47fd5p-3, 0x1.b65e2e3beee05p-1, 0x1.3dfc2b0ecc62ap-3, \
+  0x1.b37484ad806cep-1, 0x1.4ba36f39a55e5p-3, 0x1.b094b31d922a4p-1, 0x1.59338d9982085p-3, \
+  0x1.adbe87f94905ep-1, 0x1.66acd4272ad51p-3, 0x1.aaf1d2f87ebfdp-1, 0x1.740f8f54037a3p-3, \
+  0x1.a82e65130e159p-1, 0x1.815c0a14357e9p-3, 0x1.a574107688a4ap-1, 0x1.8e928de886d41p-3, \
+  0x1.a2c2a87c51ca0p-1, 0x1.9bb362e7dfb85p-3, 0x1.a01a01a01a01ap-1, 0x1.a8becfc882f19p-3, \
+  0x1.9d79f176b682dp-1, 0x1.b5b519e8fb5a6p-3, 0x1.9ae24ea5510dap-1, 0x1.c2968558c18c2p-3, \
+  0x1.9852f0d8ec0ffp-1, 0x1.cf6354e09c5ddp-3, 0x1.95cbb0be377aep-1, 0x1.dc1bca0abec7bp-3, \
+  0x1.934c67f9b2ce6p-1, 0x1.e8c0252aa5a60p-3, 0x1.90d4f120190d5p-1, 0x1.f550a564b7b37p-3, \
+  0x1.8e6527af1373fp-1, 0x1.00e6c45ad501dp-2, 0x1.8bfce8062ff3ap-1, 0x1.071b85fcd590dp-2, \
+  0x1.899c0f601899cp-1, 0x1.0d46b579ab74bp-2, 0x1.87427bcc092b9p-1, 0x1.136870293a8b0p-2, \
+  0x1.84f00c2780614p-1, 0x1.1980d2dd4236fp-2, 0x1.82a4a0182a4a0p-1, 0x1.1f8ff9e48a2f3p-2, \
+  0x1.8060180601806p-1, 0x1.2596010df763ap-2, 0x1.7e225515a4f1dp-1, 0x1.2b9303ab89d25p-2, \
+  0x1.7beb3922e017cp-1, 0x1.31871c9544185p-2, 0x1.79baa6bb6398bp-1, 0x1.3772662bfd85cp-2, \
+  0x1.77908119ac60dp-1, 0x1.3d54fa5c1f710p-2, 0x1.756cac201756dp-1, 0x1.432ef2a04e813p-2, \
+  0x1.734f0c541fe8dp-1, 0x1.49006804009d0p-2, 0x1.713786d9c7c09p-1, 0x1.4ec9732600269p-2, \
+  0x1.6f26016f26017p-1, 0x1.548a2c3add263p-2, 0x1.6d1a62681c861p-1, 0x1.5a42ab0f4cfe2p-2, \
+  0x1.6b1490aa31a3dp-1, 0x1.5ff3070a793d4p-2, 0x1.691473a88d0c0p-1, 0x1.659b57303e1f2p-2, \
+  0x1.6719f3601671ap-1, 0x1.6b3bb2235943dp-2, 0x1.6524f853b4aa3p-1, 0x1.70d42e2789236p-2, \
+  0x1.63356b88ac0dep-1, 0x1.7664e1239dbcfp-2, 0x1.614b36831ae94p-1, 0x1.7bede0a37afbfp-2, \
+  0x1.5f66434292dfcp-1, 0x1.816f41da0d495p-2, 0x1.5d867c3ece2a5p-1, 0x1.86e919a330ba1p-2, \
+  0x1.5babcc647fa91p-1, 0x1.8c5b7c858b48bp-2, 0x1.59d61f123ccaap-1, 0x1.91c67eb45a83ep-2, \
+  0x1.5805601580560p-1, 0x1.972a341135159p-2, 0x1.56397ba7c52e2p-1, 0x1.9c86b02dc0862p-2, \
+  0x1.54725e6bb82fep-1, 0x1.a1dc064d5b995p-2, 0x1.52aff56a8054bp-1, 0x1.a72a4966bd9e9p-2, \
+  0x1.50f22e111c4c5p-1, 0x1.ac718c258b0e5p-2, 0x1.4f38f62dd4c9bp-1, 0x1.b1b1e0ebdfc5ap-2, \
+  0x1.4d843bedc2c4cp-1, 0x1.b6eb59d3cf35cp-2, 0x1.4bd3edda68fe1p-1, 0x1.bc1e08b0dad0ap-2, \
+  0x1.4a27fad76014ap-1, 0x1.c149ff115f027p-2, 0x1.4880522014880p-1, 0x1.c66f4e3ff6ff9p-2, \
+  0x1.46dce34596066p-1, 0x1.cb8e0744d7acap-2, 0x1.453d9e2c776cap-1, 0x1.d0a63ae721e64p-2, \
+  0x1.43a2730abee4dp-1, 0x1.d5b7f9ae2c684p-2, 0x1.420b5265e5951p-1, 0x1.dac353e2c5955p-2, \
+  0x1.40782d10e6566p-1, 0x1.dfc859906d5b5p-2, 0x1.3ee8f42a5af07p-1, 0x1.e4c71a8687704p-2, \
+  0x1.3d5d991aa75c6p-1, 0x1.e9bfa659861f5p-2, 0x1.3bd60d9232955p-1, 0x1.eeb20c640ddf3p-2, \
+  0x1.3a524387ac822p-1, 0x1.f39e5bc811e5dp-2, 0x1.38d22d366088ep-1, 0x1.f884a36fe9ec1p-2, \
+  0x1.3755bd1c945eep-1, 0x1.fd64f20f61571p-2, 0x1.35dce5f9f2af8p-1, 0x1.011fab125ff8ap-1, \
+  0x1.34679ace01346p-1, 0x1.0389eefce633cp-1, 0x1.32f5ced6a1dfap-1, 0x1.05f14bd26459cp-1, \
+  0x1.3187758e9ebb6p-1, 0x1.0855c884b450ep-1, 0x1.301c82ac40260p-1, 0x1.0ab76bece14d2p-1, \
+  0x1.2eb4ea1fed14bp-1, 0x1.0d163ccb9d6b8p-1, 0x1.2d50a012d50a0p-1, 0x1.0f7241c9b497dp-1, \
+  0x1.2bef98e5a3711p-1, 0x1.11cb81787ccf8p-1, 0x1.2a91c92f3c105p-1, 0x1.1422025243d45p-1, \
+  0x1.293725bb804a5p-1, 0x1.1675cababa60ep-1, 0x1.27dfa38a1ce4dp-1, 0x1.18c6e0ff5cf07p-1, \
+  0x1.268b37cd60127p-1, 0x1.1b154b57da29ep-1, 0x1.2539d7e9177b2p-1, 0x1.1d610fe677003p-1, \
+  0x1.23eb79717605bp-1, 0x1.1faa34b87094cp-1, 0x1.22a0122a0122ap-1, 0x1.21f0bfc65beecp-1, \
+  0x1.21579804855e6p-1, 0x1.2434b6f483934p-1, 0x1.2012012012012p-1, 0x1.26762013430e0p-1, \
+  0x1.1ecf43c7fb84cp-1, 0x1.28b500df60783p-1, 0x1.1d8f5672e4abdp-1, 0x1.2af15f02640acp-1, \
+  0x1.1c522fc1ce059p-1, 0x1.2d2b4012edc9dp-1, 0x1.1b17c67f2bae3p-1, 0x1.2f62a99509546p-1, \
+  0x1.19e0119e0119ep-1, 0x1.3197a0fa7fe6ap-1, 0x1.18ab083902bdbp-1, 0x1.33ca2ba328994p-1, \
+  0x1.1778a191bd684p-1, 0x1.35fa4edd36ea0p-1, 0x1.1648d50fc3201p-1, 0x1.38280fe58797fp-1, \
+  0x1.151b9a3fdd5c9p-1, 0x1.3a5373e7ebdf9p-1, 0x1.13f0e8d344724p-1, 0x1.3c7c7fff73206p-1, \
+  0x1.12c8b89edc0acp-1, 0x1.3ea33936b2f5bp-1, 0x1.11a3019a74826p-1, 0x1.40c7a4880dceap-1, \
+  0x1.107fbbe011080p-1, 0x1.42e9c6ddf80bfp-1, 0x1.0f5edfab325a2p-1, 0x1.4509a5133bb0ap-1, \
+  0x1.0e40655826011p-1, 0x1.472743f33aaadp-1, 0x1.0d24456359e3ap-1, 0x1.4942a83a2fc07p-1, \
+  0x1.0c0a7868b4171p-1, 0x1.4b5bd6956e273p-1, 0x1.0af2f722eecb5p-1, 0x1.4d72d3a39fd01p-1, \
+  0x1.09ddba6af8360p-1, 0x1.4f87a3f5026e9p-1, 0x1.08cabb37565e2p-1, 0x1.519a4c0ba3446p-1, \
+  0x1.07b9f29b8eae2p-1, 0x1.53aad05b99b7cp-1, 0x1.06ab59c7912fbp-1, 0x1.55b9354b40bcep-1, \
+  0x1.059eea0727586p-1, 0x1.57c57f336f191p-1, 0x1.04949cc1664c5p-1, 0x1.59cfb25fae87fp-1, \
+  0x1.038c6b78247fcp-1, 0x1.5bd7d30e71c73p-1, 0x1.02864fc7729e9p-1, 0x1.5ddde57149923p-1, \
+  0x1.0182436517a37p-1, 0x1.5fe1edad18919p-1, 0x1.0080402010080p-1, 0x1.61e3efda46467p-1
+
+#if defined(__CUDACC__)
+static __device__ const double k_log_tab_d[256] = {CLOUDSC_LOG_TAB_VALUES};
+#else
+static const double k_log_tab_h[256] = {CLOUDSC_LOG_TAB_VALUES};
+#endif
+CLOUDSC_FN double log_tab(double x) {
+#if defined(__CUDACC__)
+  const int hi = __double2hiint(x);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 tv = __ldg(reinterpret_cast<const double2 *>(k_log_tab_d) + ((hi >> 13) & 127));
+  const double invc = tv.x, logc = tv.y;
+  const double r = fma(m, invc, -1.0);
+#else
+  long long xb;
+  std::memcpy(&xb, &x, 8);
+  const int hi = (int)(xb >> 32);
+  double m;
+  xb = (xb & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+  std::memcpy(&m, &xb, 8);
+  const double invc = k_log_tab_h[2 * ((hi >> 13) & 127)], logc = k_log_tab_h[2 * ((hi >> 13) & 127) + 1];
+  const double r = std::fma(m, invc, -1.0);
+#endif
+  const double fe = (double)((hi >> 20) - 1023);
+  const double r2 = r * r;
+  const double p = r * 0.33333333333333331 - 0.5;
+  const double q = r * 0.2 - 0.25;
+  const double t = r2 * -0.16666666666666666 + q;
+  const double u = r2 * t + p;
+  const double l = r2 * u + r;                /* log1p(r) */
+  return (fe * 6.93147180369123816490e-01 + logc) + (fe * 1.90821492927058770002e-10 + l);
+}
 /* x^y for x > 0 as exp(y log x): relative error ~ |y log x| * 2e-16 (library pow: 0.5 ulp at ~15x the
  * instructions and a call into a spilling slow path).  exp_fast is declared above. */
+#if CLOUDSC_LOG_TABLE
+CLOUDSC_FN double pow_fast(double x, double y) { return exp_fast_lo(y * log_tab(x)); }
+#else
 CLOUDSC_FN double pow_fast(double x, double y) { return exp_fast_lo(y * log_fast(x)); }
+#endif
 /* x^y = 2^(y lg2 x) on the special-function unit: relative error ~ |y lg2 x| * 2^-22; x = 0 gives 2^-inf = 0 */
 CLOUDSC_FN float pow_fast(float x, float y) {
 #if defined(__CUDACC__)
@@ -350,6 +462,26 @@ CLOUDSC_FN float sqrt_fast(float x) {
 #endif
 }
 
+/* max(x, 0).  Fast mode, double, device: a test of the sign bit on the integer pipe (ISETP + 2 SEL) instead of a compare
+ * on the FP64 pipe (DSETP + 2 FSEL); same value for every non-NaN x (-0 gives +0 either way). */
+#ifndef CLOUDSC_MX0_INT
+#define CLOUDSC_MX0_INT 0
+#endif
+CLOUDSC_FN double mx0_fast(double x) {
+#if defined(__CUDACC__) && CLOUDSC_MX0_INT
+  return __double2hiint(x) < 0 ? 0.0 : x;
+#else
+  return x > 0.0 ? x : 0.0;
+#endif
+}
+CLOUDSC_FN float mx0_fast(float x) { return mx(x, 0.0f); }
+#if CLOUDSC_STRICT
+#define CLOUDSC_MX0(x) mx((x), zero)
+#define CLOUDSC_MX0R(x) mx(zero, (x))
+#else
+#define CLOUDSC_MX0(x) mx0_fast(x)
+#define CLOUDSC_MX0R(x) mx0_fast(x)
+#endif
 #if CLOUDSC_STRICT
 #define CLOUDSC_RCP(x) (one / (x))
 #define CLOUDSC_DIV(a, b) ((a) / (b))
@@ -376,7 +508,7 @@ template <typename T> CLOUDSC_FN T ex_lo(T x) { return ex_lib(x); }
 #define CLOUDSC_CALLS 0
 #endif
 #if CLOUDSC_CALLS && defined(__CUDACC__)
-__device__ __noinline__ double pow_call(double x, double y) { return exp_fast_lo(y * log_fast(x)); }
+__device__ __noinline__ double pow_call(double x, double y) { return pow_fast(x, y); }
 __device__ __noinline__ double exp_call(double x) { return exp_fast(x); }
 __device__ __noinline__ double exp_lo_call(double x) { return exp_fast_lo(x); }
 CLOUDSC_FN float pow_call(float x, float y) { return pow_fast(x, y); }
@@ -528,11 +660,22 @@ CLOUDSC_FN void sink_limiter(const CloudscConst<T> &c, T &a01, T &a02, T &a03, T
                              T &d0, T &d1, T &d2, T &d3, const T (&qx)[4], const T qv, T &cs0, T &cs1, T &cs2, T &cs3, T &cs4) {
   const T zero = T(0.0);
       /* column sums sum_n zsolqa[n][m], n = 0..4 in the reference's order (:2239, :2330) */
+#if CLOUDSC_STRICT || defined(CLOUDSC_NOTRIM)
 #define CLOUDSC_COLSUM0 ((((zero + d0) - a01) - a02) - a03) - a04
 #define CLOUDSC_COLSUM1 (((zero + a01) + d1) - a12) - a14
 #define CLOUDSC_COLSUM2 ((((zero + a02) + a12) + d2) - a23) - a24
 #define CLOUDSC_COLSUM3 (((zero + a03) + a23) + d3) - a34
 #define CLOUDSC_COLSUM4 (((zero + a04) + a14) + a24) + a34
+#define CLOUDSC_NEG(x) (zero - (x))
+#else
+/* (0 + x and 0 - x as x and -x: the same values, signs of zeros aside, without the additions) */
+#define CLOUDSC_COLSUM0 (((d0 - a01) - a02) - a03) - a04
+#define CLOUDSC_COLSUM1 ((a01 + d1) - a12) - a14
+#define CLOUDSC_COLSUM2 (((a02 + a12) + d2) - a23) - a24
+#define CLOUDSC_COLSUM3 ((a03 + a23) + d3) - a34
+#define CLOUDSC_COLSUM4 ((a04 + a14) + a24) + a34
+#define CLOUDSC_NEG(x) (-(x))
+#endif
       /* "if zsolqa[n][m] < 0 scale the pair": a_nm itself for n < m, a_mn > 0 for n > m; a negative
        * diagonal is scaled twice (n == m hits both statements of :2281-2282) */
 #define CLOUDSC_SCALE_LO(a) if ((a) < zero) (a) = (a) * ratio
@@ -546,28 +689,28 @@ CLOUDSC_FN void sink_limiter(const CloudscConst<T> &c, T &a01, T &a02, T &a03, T
       cs0 = CLOUDSC_COLSUM0; cs1 = CLOUDSC_COLSUM1; cs2 = CLOUDSC_COLSUM2; cs3 = CLOUDSC_COLSUM3; cs4 = CLOUDSC_COLSUM4;
       const T mm0 = mx(qx[0], c.zepsec), mm1 = mx(qx[1], c.zepsec), mm2 = mx(qx[2], c.zepsec), mm3 = mx(qx[3], c.zepsec),
               mm4 = mx(qv, c.zepsec);
-      if (CLOUDSC_RARE((zero - cs0 > mm0) | (zero - cs1 > mm1) | (zero - cs2 > mm2) | (zero - cs3 > mm3) | (zero - cs4 > mm4))) {
-        T sinksum = zero - cs0;
+      if (CLOUDSC_RARE((CLOUDSC_NEG(cs0) > mm0) | (CLOUDSC_NEG(cs1) > mm1) | (CLOUDSC_NEG(cs2) > mm2) | (CLOUDSC_NEG(cs3) > mm3) | (CLOUDSC_NEG(cs4) > mm4))) {
+        T sinksum = CLOUDSC_NEG(cs0);
         if (sinksum > mm0) {
           const T ratio = CLOUDSC_DIV(mm0, sinksum);
           CLOUDSC_SCALE_D(d0); CLOUDSC_SCALE_HI(a01); CLOUDSC_SCALE_HI(a02); CLOUDSC_SCALE_HI(a03); CLOUDSC_SCALE_HI(a04);
         }
-        sinksum = zero - (CLOUDSC_COLSUM1);
+        sinksum = CLOUDSC_NEG(CLOUDSC_COLSUM1);
         if (sinksum > mm1) {
           const T ratio = CLOUDSC_DIV(mm1, sinksum);
           CLOUDSC_SCALE_LO(a01); CLOUDSC_SCALE_D(d1); CLOUDSC_SCALE_HI(a12); CLOUDSC_SCALE_HI(a14);
         }
-        sinksum = zero - (CLOUDSC_COLSUM2);
+        sinksum = CLOUDSC_NEG(CLOUDSC_COLSUM2);
         if (sinksum > mm2) {
           const T ratio = CLOUDSC_DIV(mm2, sinksum);
           CLOUDSC_SCALE_LO(a02); CLOUDSC_SCALE_LO(a12); CLOUDSC_SCALE_D(d2); CLOUDSC_SCALE_HI(a23); CLOUDSC_SCALE_HI(a24);
         }
-        sinksum = zero - (CLOUDSC_COLSUM3);
+        sinksum = CLOUDSC_NEG(CLOUDSC_COLSUM3);
         if (sinksum > mm3) {
           const T ratio = CLOUDSC_DIV(mm3, sinksum);
           CLOUDSC_SCALE_LO(a03); CLOUDSC_SCALE_LO(a23); CLOUDSC_SCALE_D(d3); CLOUDSC_SCALE_HI(a34);
         }
-        sinksum = zero - (CLOUDSC_COLSUM4);
+        sinksum = CLOUDSC_NEG(CLOUDSC_COLSUM4);
         if (sinksum > mm4) {
           const T ratio = CLOUDSC_DIV(mm4, sinksum);
           CLOUDSC_SCALE_LO(a04); CLOUDSC_SCALE_LO(a14); CLOUDSC_SCALE_LO(a24); CLOUDSC_SCALE_LO(a34);
@@ -582,6 +725,7 @@ CLOUDSC_FN void sink_limiter(const CloudscConst<T> &c, T &a01, T &a02, T &a03, T
 #undef CLOUDSC_SCALE_LO
 #undef CLOUDSC_SCALE_HI
 #undef CLOUDSC_SCALE_D
+#undef CLOUDSC_NEG
 }
 
 /*
@@ -602,7 +746,11 @@ CLOUDSC_FN void implicit_solve(const CloudscConst<T> &c, const T (&qx)[4], const
       qxn[3] = qx[3] + cs3;
       qxn[4] = qv + cs4;
       {
+#if CLOUDSC_STRICT || defined(CLOUDSC_NOTRIM)
         const T den0 = ((one + zero) + qb00) + qb03;
+#else
+        const T den0 = (one + qb00) + qb03;
+#endif
         const T den1 = ((one + fallsink1) + qb11) + qb13;
         const T den2 = one + fallsink2;
         const T den3 = one + fallsink3;
@@ -754,7 +902,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
     /* ---- FOEALFA of this level (:588; also needed by the flux section at every level) */
     const T alfa_w = foealfa(c, t);
     /* ---- cloud fraction in [0,1], :625 */
-    a = mx(zero, mn(one, a));
+    a = CLOUDSC_MX0R(mn(one, a));
 
     /* values of this level the flux section needs (zqxn2d stays 0 above ncldtop, :503) */
     T qxn2d[4] = {zero, zero, zero, zero};
@@ -775,7 +923,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T foeewmt = mn(CLOUDSC_DIVR(c.r2es * (alfa_w * e_liq + (one - alfa_w) * e_ice), pap, r_pap), T(0.5));
       const T cor_m = CLOUDSC_RCP(one - c.retv * foeewmt);
       const T qsmix = CLOUDSC_DIVR(foeewmt, one - c.retv * foeewmt, cor_m);
-      const T zalfa = mx(zero, cs(one, t - c.rtt));
+      const T zalfa = CLOUDSC_MX0R(cs(one, t - c.rtt));
       /* (the reference applies min(0.5, .) twice here; the second one is the identity) */
       const T foeew = mn(CLOUDSC_DIVR(zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice), pap, r_pap), T(0.5));
       const T cor_i = CLOUDSC_RCP(one - c.retv * foeew);
@@ -833,7 +981,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T facm = alfa_w * facw + (one - alfa_w) * faci;
       const T dqsmixdt = (facm * cor_m) * qsmix;
       const T corqsmix = one + foeldcpm(c, alfa_w) * dqsmixdt;
-      const T evaplimmix = mx(CLOUDSC_DIV(qsmix - qv, corqsmix), zero);
+      const T evaplimmix = CLOUDSC_MX0(CLOUDSC_DIV(qsmix - qv, corqsmix));
       /* in-cloud condensate, :837-840 */
       const T tmpa = CLOUDSC_RCP(mx(a, c.zepsec));
       T liqcld = qx[0] * tmpa;
@@ -857,7 +1005,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       T qe_nc;                                         /* zqe of :1275-1302 */
       if (c.nssopt == 0 || c.nssopt == 1) {
         qe_nc = CLOUDSC_DIVR(qv - a * qsice, mx(c.zepsec, one_m_a), r_1ma);
-        qe_nc = mx(zero, qe_nc);
+        qe_nc = CLOUDSC_MX0R(qe_nc);
       } else if (c.nssopt == 2) {
         qe_nc = qv;
       } else {
@@ -886,7 +1034,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         tn = mx(tn, T(160.0));
         T qsm = qsmix;
 #if CLOUDSC_DEPOS_EARLY && !CLOUDSC_STRICT
-        if (qx[0] > c.rlmin && t < c.rtt) {
+#if CLOUDSC_DEPOS_EARLY == 1
+        if (qx[0] > c.rlmin && t < c.rtt)
+#endif
+        { /* (== 2: for every lane that is here, without a branch -- the values are only read where 3.7 applies) */
           deposition_prep<T>(c, ptsphy, t, pap, rho, r_rho, r_t, e_ice, fokoop, icecld, dep_inew, dep_ice0, dep_infactor);
           dep_ready = true;
         }
@@ -906,10 +1057,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         else { fac = a + fokoop * one_m_a; facI = sc.faci_koop; }
         T supsat;
         if (a > sc.one_m_ramin) {
-          supsat = mx(CLOUDSC_DIVR(qv - fac * qsice, corqsice, r_corqsice), zero);
+          supsat = CLOUDSC_MX0(CLOUDSC_DIVR(qv - fac * qsice, corqsice, r_corqsice));
         } else {
           const T qp1env = CLOUDSC_DIV(qv - a * qsice, mx(one_m_a, c.zepsilon));
-          supsat = mx(CLOUDSC_DIVR(one_m_a * (qp1env - fac * qsice), corqsice, r_corqsice), zero);
+          supsat = CLOUDSC_MX0(CLOUDSC_DIVR(one_m_a * (qp1env - fac * qsice), corqsice, r_corqsice));
         }
         if (CLOUDSC_RARE(supsat > c.zepsec)) {
           if (t > c.rthomo) { a04 = a04 - supsat; qxfg[0] = qxfg[0] + supsat; }
@@ -942,7 +1093,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 
       /* ================= 3.3 subsidence compensating convective updraughts, :1002-1075 ==== */
       if (k > ktop) {
-        const T mf = mx(zero, s.mf_k * dtgdp);
+        const T mf = CLOUDSC_MX0R(s.mf_k * dtgdp);
         T acust = mf * s.anewm1;
         const T lcust0 = mf * s.qlnm1, lcust1 = mf * s.qinm1;
         convsrce0 = convsrce0 + lcust0;
@@ -952,12 +1103,12 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         const T dqs_s = (s.anewm1 * dtforc) * dqsmixdt;
         T lfinalsum = zero;
         {
-          T lfinal = mx(zero, lcust0 - dqs_s);
+          T lfinal = CLOUDSC_MX0R(lcust0 - dqs_s);
           T evap = mn(lcust0 - lfinal, evaplimmix);
           lfinal = lcust0 - evap;
           lfinalsum = lfinalsum + lfinal;
           d0 = d0 + lcust0; a04 = a04 + evap;
-          lfinal = mx(zero, lcust1 - dqs_s);
+          lfinal = CLOUDSC_MX0R(lcust1 - dqs_s);
           evap = mn(lcust1 - lfinal, evaplimmix);
           lfinal = lcust1 - evap;
           lfinalsum = lfinalsum + lfinal;
@@ -967,7 +1118,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         solac = solac + acust;
       }
       if (k + 1 < klev) { /* subsidence sink, :1064-1075 */
-        const T mfdn = mx(zero, mf_n * dtgdp);
+        const T mfdn = CLOUDSC_MX0R(mf_n * dtgdp);
         solab = solab + mfdn;
         qb00 = qb00 + mfdn;
         qb11 = qb11 + mfdn;
@@ -978,7 +1129,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       {
         const T ldifdt = (ktype > 0 && plude_out > c.zepsec) ? sc.ldifdt_conv : sc.ldifdt;
         if (li > c.zepsec) {
-          const T e = ldifdt * mx(qsmix - qv, zero);
+          const T e = ldifdt * CLOUDSC_MX0(qsmix - qv);
           T leros = a * e;
           leros = mn(leros, evaplimmix);
           leros = mn(leros, li);
@@ -993,13 +1144,13 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       if (dqs > zero) {
         T levap = a * mn(dqs, licld);
         levap = mn(levap, evaplimmix);
-        levap = mn(levap, mx(qsmix - qv, zero));
+        levap = mn(levap, CLOUDSC_MX0(qsmix - qv));
         a04 = a04 + liqfrac * levap;
         a14 = a14 + icefrac * levap;
       }
       /* 3.4b (1) increase of cloud water in existing clouds, :1214-1248 */
       if (dqs <= -c.rlmin && a > c.zepsec) {
-        T lcond1 = mx(-dqs, zero);
+        T lcond1 = CLOUDSC_MX0(-dqs);
         T cdmax;
         if (a > c.p099) {
           const T corm = CLOUDSC_RCP(one - c.retv * qsmix);
@@ -1012,7 +1163,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         } else {
           cdmax = CLOUDSC_DIV(qv - a * qsmix, a);
         }
-        lcond1 = mx(mn(lcond1, cdmax), zero);
+        lcond1 = CLOUDSC_MX0(mn(lcond1, cdmax));
         lcond1 = a * lcond1;
         if (lcond1 < c.rlmin) lcond1 = zero;
         if (t > c.rthomo) { a04 = a04 - lcond1; qxfg[0] = qxfg[0] + lcond1; }
@@ -1030,7 +1181,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
             const T lcondlim = ((a - one) * fac) * dqs - fac * qsice + qv;
             lcond2 = mn(lcond2, lcondlim);
           }
-          lcond2 = mx(lcond2, zero);
+          lcond2 = CLOUDSC_MX0(lcond2);
           if (one_m_a < c.zepsec || lcond2 < c.rlmin) { lcond2 = zero; acond = zero; }
           if (lcond2 == zero) acond = zero;
           solac = solac + acond;
@@ -1051,7 +1202,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       if (qxfg[0] > c.rlmin && t < c.rtt) {
         if (!dep_ready) deposition_prep<T>(c, ptsphy, t, pap, rho, r_rho, r_t, e_ice, fokoop, icecld, dep_inew, dep_ice0, dep_infactor);
         const T inew = dep_inew, ice0 = dep_ice0, infactor = dep_infactor;
-        T depos = mx(a * (inew - ice0), zero);
+        T depos = CLOUDSC_MX0(a * (inew - ice0));
         depos = mn(depos, qxfg[0]);
         depos = depos * mn(infactor + (one - infactor) * (c.rdepliqrefrate + CLOUDSC_DIVR(s.cldtopdist, c.rdepliqrefdepth, c.r_rdepliqrefdepth)), one);
         a01 = a01 + depos;
@@ -1087,7 +1238,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       if (qpretot > c.zepsec) {
         s.covptot = one - CLOUDSC_DIV((one - s.covptot) * (one - mx(a, s.a_m1)), one - mn(s.a_m1, c.one_m_1em6));
         s.covptot = mx(s.covptot, c.rcovpmin);
-        covpclr = mx(zero, s.covptot - a);
+        covpclr = CLOUDSC_MX0R(s.covptot - a);
         const T r_cov = CLOUDSC_RCP(s.covptot);
         (void)r_cov;
         raincld = CLOUDSC_DIVR(qxfg[2], s.covptot, r_cov);
@@ -1147,10 +1298,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         const T icetot = qxfg[1] + qxfg[3];
         T meltmax = zero;
         if (CLOUDSC_RARE(icetot > c.zepsec && t > c.rtt)) {
-          const T subsat = mx(qsice - qv, zero);
+          const T subsat = CLOUDSC_MX0(qsice - qv);
           const T tdmtw0 = t - c.rtt - subsat * (c.ztw1 + c.ztw2 * (pap - ztw3) - c.ztw4 * (t - ztw5));
           const T cons1 = ab(CLOUDSC_DIVR(ptsphy * (one + T(0.5) * tdmtw0), c.rtaumel, c.r_rtaumel));
-          meltmax = mx((tdmtw0 * cons1) * sc.zrldcp, zero);
+          meltmax = CLOUDSC_MX0((tdmtw0 * cons1) * sc.zrldcp);
         }
         if (CLOUDSC_RARE(icetot > c.zepsec && meltmax > c.zepsec)) {
           const T r_icetot = CLOUDSC_RCP(icetot);
@@ -1177,10 +1328,10 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
             const T lambda = CLOUDSC_POW(CLOUDSC_DIV(c.rcl_fac1, rho * qx[2]), c.rcl_fac2);
             const T temp = c.rcl_fzrab * (t - c.rtt);
             const T frz = ((ptsphy * CLOUDSC_DIVR(c.rcl_const5r, rho, r_rho)) * (CLOUDSC_EXP_COLD(temp) - one)) * CLOUDSC_POW(lambda, c.rcl_const6r);
-            frzmax = mx(frz, zero);
+            frzmax = CLOUDSC_MX0(frz);
           } else {
             const T cons1 = ab(CLOUDSC_DIVR(ptsphy * (one + T(0.5) * (c.rtt - t)), c.rtaumel, c.r_rtaumel));
-            frzmax = mx(((c.rtt - t) * cons1) * sc.zrldcp, zero);
+            frzmax = CLOUDSC_MX0(((c.rtt - t) * cons1) * sc.zrldcp);
           }
           if (frzmax > c.zepsec) {
             const T frz = mn(qx[2], frzmax);
@@ -1190,7 +1341,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       }
       /* 4.4c freezing of liquid, :1913-1928 */
       {
-        const T frzmax = mx((c.rthomo - t) * sc.zrldcp, zero);
+        const T frzmax = CLOUDSC_MX0((c.rthomo - t) * sc.zrldcp);
         if (CLOUDSC_RARE(frzmax > c.zepsec && qxfg[0] > c.zepsec)) {
           const T frz = mn(qxfg[0], frzmax);
           a01 = a01 + frz;
@@ -1209,7 +1360,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           const T cor_l = CLOUDSC_RCP(one - c.retv * foeeliqt);
           (void)cor_l;
           qsliq = CLOUDSC_DIVR(foeeliqt, one - c.retv * foeeliqt, cor_l);
-          qe = mx(zero, mn(qv, qsliq));
+          qe = CLOUDSC_MX0R(mn(qv, qsliq));
           rain_evap = qe < zzrh * qsliq;
         }
         if (CLOUDSC_RARE(rain_evap)) {
@@ -1219,7 +1370,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           const T lambda = CLOUDSC_POW(CLOUDSC_DIV(c.rcl_fac1, rho * preclr), c.rcl_fac2);
           const T evap_denom = c.rcl_cdenom1 * esatliq - c.rcl_cdenom2 * t * esatliq + (c.rcl_cdenom3 * CLOUDSC_CUBE(t)) * pap;
           const T corr2 = CLOUDSC_DIV(CLOUDSC_POW15(CLOUDSC_DIVR(t, T(273.0), c.r_273)) * T(393.0), t + T(120.0));
-          const T subsat = mx(zzrh * qsliq - qe, zero);
+          const T subsat = CLOUDSC_MX0(zzrh * qsliq - qe);
           const T beta = ((((CLOUDSC_DIV(T(0.5), qsliq) * (t * t)) * esatliq) * c.rcl_const1r) * CLOUDSC_DIV(corr2, evap_denom)) *
                          (CLOUDSC_DIV(c.p078, CLOUDSC_POW(lambda, c.rcl_const4r)) +
                           CLOUDSC_DIV(c.rcl_const2r * CLOUDSC_SQRT(rho * fallcorr), CLOUDSC_SQRT(corr2) * CLOUDSC_POW(lambda, c.rcl_const3r)));
@@ -1227,7 +1378,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           const T dpevap = CLOUDSC_DIV(((covpclr * beta) * ptsphy) * subsat, denom);
           const T evap = mn(dpevap, qxfg[2]);
           a24 = a24 + evap;
-          s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, CLOUDSC_DIV((s.covptot - a) * evap, qxfg[2])));
+          s.covptot = mx(c.rcovpmin, s.covptot - CLOUDSC_MX0R(CLOUDSC_DIV((s.covptot - a) * evap, qxfg[2])));
           qxfg[2] = qxfg[2] - evap;
         }
       }
@@ -1235,7 +1386,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       {
         const T zzrh = zzrh0;
         T qe = CLOUDSC_DIVR(qv - a * qsice, mx(c.zepsec, one_m_a), r_1ma);
-        qe = mx(zero, mn(qe, qsice));
+        qe = CLOUDSC_MX0R(mn(qe, qsice));
         if (covpclr > c.zepsec && qxfg[3] > c.zepsec && qe < zzrh * qsice) {
           const T cd = s.covptot * dtgdp;
           const T preclr = CLOUDSC_DIV(qxfg[3] * covpclr, cs(mx(ab(cd), c.zepsilon), cd));
@@ -1246,7 +1397,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           const T dpevap = dpr * dtgdp;
           const T evap = mn(dpevap, qxfg[3]);
           a34 = a34 + evap;
-          s.covptot = mx(c.rcovpmin, s.covptot - mx(zero, CLOUDSC_DIV((s.covptot - a) * evap, qxfg[3])));
+          s.covptot = mx(c.rcovpmin, s.covptot - CLOUDSC_MX0R(CLOUDSC_DIV((s.covptot - a) * evap, qxfg[3])));
           qxfg[3] = qxfg[3] - evap;
         }
       }

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for t in "$@"; do
   if [ "$t" = default ]; then unset CLOUDSC_B200_LIB; else export CLOUDSC_B200_LIB=$PWD/dwarf_p_cloudsc_b200/lib_alt/$t/libcloudsc_b200.so; fi
-  timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/alt_$t.json 2> gpurun_out/alt_$t.err
+  timeout -s KILL 300 python bench.py --steps ${ALT_STEPS:-30} --warmup 3 --no-cpu --no-e2e --no-gpu-reference ${ALT_ARGS} > gpurun_out/alt_$t.json 2> gpurun_out/alt_$t.err
   python - <<PY
 import json
 try:

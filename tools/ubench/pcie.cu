@@ -134,8 +134,73 @@ static void pattern(const std::string &mode, size_t arr_bytes, size_t chunk, int
   }
 }
 
+
+// --pattern 2 --knobs K: pattern 1 made to look like cloudsc_b200_run_host step by step, to find which property of the real
+// pipeline costs bandwidth.  K is a bit mask:
+//   1  ring dependencies: upload c waits for download c-4 (its staging buffer), download c waits for upload c
+//   2  piece = 54 NPROMA blocks of a [137][128] double field = 7 575 552 B (a multiple of 1 KB, not of 4 KB) instead of 8 MB
+//   4  every copy is a cudaMemcpy2DAsync of 54 rows: pitch = one block (140 288 B), width = 124/137 of it (row trimming)
+//   8  a host thread memsets 180 MB of pageable memory while the copies run (species-5 zeroing)
+//  16  an empty kernel on a third stream between upload c and download c
+__global__ void nop_kernel() {}
+static void pattern2(const std::string &mode, int knobs, int nin, int nout, int nchunks) {
+  cudaSetDevice(0);
+  const size_t blk = 140288, nb = 54;
+  const size_t piece = (knobs & 2) || (knobs & 4) ? nb * blk : (size_t)8 << 20;
+  const size_t width = (knobs & 4) ? (size_t)124 * 1024 : blk;
+  const size_t arr_bytes = piece * nchunks;
+  std::vector<char *> hin(nin), hout(nout);
+  for (auto &p : hin) p = (char *)alloc_host(mode, arr_bytes, true);
+  for (auto &p : hout) p = (char *)alloc_host(mode, arr_bytes, false);
+  char *d_up, *d_dn;
+  cudaMalloc(&d_up, 4 * piece * nin); cudaMalloc(&d_dn, 4 * piece * nout);
+  cudaStream_t s1, s2, s3;
+  cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking);
+  cudaEvent_t a1, b1, a2, b2, up[4], dn[4], kk[4];
+  cudaEventCreate(&a1); cudaEventCreate(&b1); cudaEventCreate(&a2); cudaEventCreate(&b2);
+  for (int i = 0; i < 4; ++i) { cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&dn[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&kk[i], cudaEventDisableTiming); }
+  char *scratch = (char *)malloc((size_t)180 << 20);
+  for (int rep = 0; rep < 3; ++rep) {
+    std::thread ms;
+    cudaEventRecord(a1, s1); cudaEventRecord(a2, s2);
+    for (int c = 0; c < nchunks; ++c) {
+      const int l = c % 4;
+      char *du = d_up + (size_t)l * piece * nin, *dd = d_dn + (size_t)l * piece * nout;
+      if ((knobs & 1) && c >= 4) cudaStreamWaitEvent(s1, dn[l], 0);
+      for (int f = 0; f < nin; ++f) {
+        if (knobs & 4) cudaMemcpy2DAsync(du + (size_t)f * piece, blk, hin[f] + (size_t)c * piece, blk, width, nb, cudaMemcpyHostToDevice, s1);
+        else cudaMemcpyAsync(du + (size_t)f * piece, hin[f] + (size_t)c * piece, piece, cudaMemcpyHostToDevice, s1);
+      }
+      if (knobs & 1) cudaEventRecord(up[l], s1);
+      if (knobs & 16) {
+        if (knobs & 1) cudaStreamWaitEvent(s3, up[l], 0);
+        nop_kernel<<<1, 32, 0, s3>>>();
+        cudaEventRecord(kk[l], s3);
+        if (knobs & 1) cudaStreamWaitEvent(s2, kk[l], 0);
+      } else if (knobs & 1) cudaStreamWaitEvent(s2, up[l], 0);
+      for (int f = 0; f < nout; ++f) {
+        if (knobs & 4) cudaMemcpy2DAsync(hout[f] + (size_t)c * piece, blk, dd + (size_t)f * piece, blk, width, nb, cudaMemcpyDeviceToHost, s2);
+        else cudaMemcpyAsync(hout[f] + (size_t)c * piece, dd + (size_t)f * piece, piece, cudaMemcpyDeviceToHost, s2);
+      }
+      if (knobs & 1) cudaEventRecord(dn[l], s2);
+    }
+    if (knobs & 8) ms = std::thread([&] { memset(scratch, rep, (size_t)180 << 20); });
+    cudaEventRecord(b1, s1); cudaEventRecord(b2, s2);
+    cudaEventSynchronize(b1); cudaEventSynchronize(b2);
+    if (ms.joinable()) ms.join();
+    float m1, m2; cudaEventElapsedTime(&m1, a1, b1); cudaEventElapsedTime(&m2, a2, b2);
+    const double per = (double)((knobs & 4) ? width * nb : piece);
+    const double upb = (double)nin * nchunks * per, dnb = (double)nout * nchunks * per;
+    printf("  pattern2 %-9s knobs %2d rep %d: %d+%d arrays, %d chunks: H2D %.2f GB in %.1f ms (%.1f GB/s), D2H %.2f GB in %.1f ms (%.1f GB/s), sum %.1f GB/s over %.1f ms\n",
+           mode.c_str(), knobs, rep, nin, nout, nchunks, upb / 1e9, m1, upb / m1 / 1e6, dnb / 1e9, m2, dnb / m2 / 1e6, (upb + dnb) / std::max(m1, m2) / 1e6, std::max(m1, m2));
+  }
+  for (auto p : hin) cudaFreeHost(p);
+  for (auto p : hout) cudaFreeHost(p);
+  cudaFree(d_up); cudaFree(d_dn); free(scratch);
+}
+
 int main(int argc, char **argv) {
-  int ngpu = 1, reps = 3, bind = 0, pat = 0, nin = 35, nout = 22;
+  int ngpu = 1, reps = 3, bind = 0, pat = 0, nin = 35, nout = 22, knobs = 0, nchunks = 24;
   size_t mb = 1024, chunk_mb = 0;
   std::string mode = "all";
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -149,11 +214,14 @@ int main(int argc, char **argv) {
     else if (a == "--pattern") pat = atoi(argv[i + 1]);
     else if (a == "--nin") nin = atoi(argv[i + 1]);
     else if (a == "--nout") nout = atoi(argv[i + 1]);
+    else if (a == "--knobs") knobs = atoi(argv[i + 1]);
+    else if (a == "--nchunks") nchunks = atoi(argv[i + 1]);
   }
   int have = 0;
   cudaGetDeviceCount(&have);
   if (have < 1) { fprintf(stderr, "no CUDA device\n"); return 1; }
   if (ngpu > have) ngpu = have;
+  if (pat == 2) { pattern2(mode == "all" ? "hostalloc" : mode, knobs, nin, nout, nchunks); return 0; }
   if (pat) {
     for (const std::string &m : (mode == "all" ? std::vector<std::string>{"hostalloc", "thp"} : std::vector<std::string>{mode}))
       pattern(m, mb << 20, (chunk_mb ? chunk_mb : 8) << 20, nin, nout);
