@@ -490,18 +490,21 @@ int cloudsc_b200_destroy(cloudsc_b200_state *st) {
  *   mode 2  streaming: 12 persistent warps per SM taking tiles from a queue, the input ring kept full across tiles
  *   mode 1  persistent: 12 warps per SM, each running its tiles in two pieces (levels [0, ksplit) and [ksplit, klev))
  *           and choosing the next piece so that about target_b of the SM's warps are in a lower piece at any time
+ *   mode 3  staggered streaming: mode 2, but the first tile of slot j of an SM is only swept down to the level where
+ *           j/nslots of a tile's time has passed (target_b = nslots, <= 0: all resident warps); the remainders are the
+ *           last phase of the launch, longest first -- the SM's warps are spread over the sweep from the first cycle
  * ksplit <= 0 -> 3*klev/5; target_b <= 0 -> 7 of 12.  Results are bit-identical in every mode.
  */
 int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b) {
   if (!st) return fail(CLOUDSC_B200_EARG, "set_schedule: NULL state");
-  if (mode < 0 || mode > 2) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
+  if (mode < 0 || mode > 3) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
   if (ksplit >= st->klev) return fail(CLOUDSC_B200_EARG, "set_schedule: ksplit must be below klev");
   if (int rc = state_on_current_device(st, "set_schedule")) return rc;
   if (mode >= 1 && st->has_tm && !st->sched.carry) {
     const int ntiles = (st->nblocks * st->nproma + 31) / 32;
     CU(cudaMalloc(&st->sched.carry, persist_carry_bytes(ntiles, st->precision)));
-    CU(cudaMalloc((void **)&st->sched.sm_b, 1024 * sizeof(int)));
-    CU(cudaMemset(st->sched.sm_b, 0, 1024 * sizeof(int)));
+    CU(cudaMalloc((void **)&st->sched.sm_b, kSchedInts * sizeof(int)));
+    CU(cudaMemset(st->sched.sm_b, 0, kSchedInts * sizeof(int)));
     st->sched.carry_tiles = ntiles;
   }
   st->sched_mode = mode;

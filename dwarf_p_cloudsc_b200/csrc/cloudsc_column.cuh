@@ -465,7 +465,7 @@ CLOUDSC_FN float sqrt_fast(float x) {
 /* max(x, 0).  Fast mode, double, device: a test of the sign bit on the integer pipe (ISETP + 2 SEL) instead of a compare
  * on the FP64 pipe (DSETP + 2 FSEL); same value for every non-NaN x (-0 gives +0 either way). */
 #ifndef CLOUDSC_MX0_INT
-#define CLOUDSC_MX0_INT 0
+#define CLOUDSC_MX0_INT 1
 #endif
 CLOUDSC_FN double mx0_fast(double x) {
 #if defined(__CUDACC__) && CLOUDSC_MX0_INT

@@ -645,6 +645,105 @@ cloudsc_sweep_stream(const __grid_constant__ FieldTable ft, const __grid_constan
   }
 }
 
+/* ---- staggered streaming kernel: persistent warps, tile queue, the warps of an SM spread over the sweep from the start -- */
+/*
+ * Schedule mode 3.  With one CTA per tile (and with modes 1/2) every resident warp starts a tile at level 0 at the same
+ * moment, so the 12 warps of an SM walk through the bandwidth-bound upper levels and then through the latency-bound cloudy
+ * levels together; the launch list shows what that costs: a 1-wave launch takes 0.69 ms, every further wave 0.64 / 0.62 /
+ * 0.60 ms as the warps drift apart, 0.58 ms in the steady state of a 12-wave launch (profiles/r2_wave_sizes.txt).  Here
+ * the warps are spread over the sweep from the first cycle on WITHOUT idling: warp w owns tile w as its first tile and has
+ * slot j = w / (gridDim.x / nslots) on its SM (the block scheduler deals CTAs round-robin over the SMs); slot 0 sweeps its
+ * first tile whole, slot j > 0 only levels [0, cut[j]) of it -- a piece that takes about j/nslots of a tile -- parks the
+ * state at the cut (the same `Carry` + parked slots as mode 1) and goes on with whole tiles from the queue.  The
+ * remainders [cut[j], klev) are the work of the last phase: when the queue is empty every warp takes remainders, longest
+ * first, so the launch also ends on pieces of 11/12 ... 1/12 of a tile instead of whole tiles.
+ *   ctl[0]  queue of whole tiles (tile = gridDim.x + ticket),  ctl[1]  queue of remainders,
+ *   ctl[2 + w]  state of first tile w: 0 untouched, 1 first piece running, 2 | cut << 8 parked at `cut`, 3 done.
+ * A first tile whose owner has not started when the remainder phase reaches it (grid not fully resident) is swept whole
+ * by whoever gets there first; nobody ever waits for a warp that is not running.  Bit-identical to mode 0.
+ */
+struct StaggerPlan {
+  int ntiles, nslots;
+  int cut[16];     /* cut[0] unused (slot 0 never cuts) */
+  void *carry;     /* [gridDim.x][kCarryVals][32] elements */
+  int *ctl;        /* 2 + gridDim.x ints, zeroed before every launch */
+};
+
+template <typename T>
+__global__ void __launch_bounds__(32, warps_per_sm<T>())
+cloudsc_sweep_stagger(const __grid_constant__ FieldTable ft, const __grid_constant__ TensorMaps tm, const LaunchGeom g,
+                      const __grid_constant__ StepConst<T> sc, const __grid_constant__ StaggerPlan plan) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using IO = TmapIO<T, true>;
+  const int w = (int)blockIdx.x, G = (int)gridDim.x;
+  const unsigned bar0 = smem_u32(smem_raw + 2 * IO::kStage);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  int staged = 0;
+  int *const state = plan.ctl + 2;
+  const int nfirst = G < plan.ntiles ? G : plan.ntiles;
+  int phase = 1;
+  for (;;) {
+    /* lane 0 picks the next piece: levels [kb, ke) of `tile`; mark = the state its first-tile entry gets afterwards (0: none) */
+    int tile = -1, kb = 0, ke = g.klev, mark = 0;
+    if (threadIdx.x == 0) {
+      if (phase == 1) {           /* 1. the first tile: whole (slot 0) or up to this slot's cut */
+        phase = 2;
+        if (w < plan.ntiles && atomicCAS(&state[w], 0, 1) == 0) {
+          const int per = G / plan.nslots > 0 ? G / plan.nslots : 1;
+          const int j = (w / per) % plan.nslots;
+          const int cut = j > 0 ? plan.cut[j] : 0;
+          tile = w;
+          if (cut > 0 && cut < g.klev) { ke = cut; mark = 2 | (cut << 8); } else mark = 3;
+        }
+      }
+      if (tile < 0 && phase == 2) {   /* 2. whole tiles from the queue */
+        const int t = G + atomicAdd(&plan.ctl[0], 1);
+        if (t < plan.ntiles) tile = t; else phase = 3;
+      }
+      while (tile < 0 && phase == 3) {   /* 3. the remainders of the first tiles, in index order = longest first */
+        const int i = atomicAdd(&plan.ctl[1], 1);
+        if (i >= nfirst) { phase = 4; break; }
+        int st = atomicCAS(&state[i], 0, 1);                   /* owner never started: take the whole tile */
+        while ((st & 0xff) == 1) { __nanosleep(200); st = atomicAdd(&state[i], 0); }   /* owner is in its first piece right now */
+        if (st == 0) { tile = i; mark = 3; }
+        else if ((st & 0xff) == 2) { tile = i; kb = st >> 8; __threadfence(); }
+      }
+    }
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile < 0) break;
+    kb = __shfl_sync(0xffffffffu, kb, 0);
+    ke = __shfl_sync(0xffffffffu, ke, 0);
+    const int ccol = g.col_begin + tile * IO::kCols;
+    const int ibl = ccol / g.nproma;
+    const int jl0 = ccol - ibl * g.nproma;
+    const int jl = jl0 + (int)threadIdx.x;
+    const long long bL = (long long)ibl * g.klev * g.nproma, bH = (long long)ibl * (g.klev + 1) * g.nproma;
+    const unsigned rows = (unsigned)kb * (unsigned)g.nproma;
+    IO io{ft, tm, ibl, jl0, g.nproma, g.klev, dev_consts<T>().ncldtop - 2,
+          smem_u32(smem_raw), bar0,
+          reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
+          bH + jl, (long long)ibl * g.nproma + jl,
+          (unsigned)(bL + jl) + rows, (unsigned)(bH + jl + g.nproma) + rows, (unsigned)(bL * 5 + jl) + rows, (unsigned)(g.klev * g.nproma),
+          ccol + (int)threadIdx.x < g.col_end, kb, ke, staged - kb,
+          static_cast<T *>(plan.carry) + (size_t)(tile < G ? tile : 0) * (kCarryVals * 32) + threadIdx.x, -1, 0};
+    if (elect_one()) {
+      io.issue(kb);
+      if (kb + 1 < ke) io.issue(kb + 1);
+    }
+    __syncwarp();
+    cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+    __threadfence();            /* every lane: its part of a parked state is visible before the entry says so */
+    __syncwarp();
+    staged += ke - kb;
+    if (threadIdx.x == 0 && mark) atomicExch(&state[tile], mark);
+  }
+}
+
 /* ---- IO policy 3: thread-private cp.async ring, pre-offset slot pointers, streaming stores -------- */
 /*
  * Every thread stages ITS OWN column: per level 27 `cp.async` (SASS LDGSTS, 8 bytes each, a warp
@@ -1030,6 +1129,42 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
   int ksplit = ps.ksplit > 0 ? ps.ksplit : (3 * g.klev) / 5;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > g.klev - 1) ksplit = g.klev - 1;
+  if (ps.mode == 3) {
+    const void *sfn = (const void *)cloudsc_sweep_stagger<T>;
+    e = cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (resident > ps.carry_tiles || 2 + resident > kStaggerCtlInts) return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
+    StaggerPlan sp;
+    sp.ntiles = ntiles;
+    sp.nslots = ps.target_b > 0 ? (ps.target_b > 16 ? 16 : ps.target_b) : per_sm[dev & 63][pi];
+    if (sp.nslots > 16) sp.nslots = 16;
+    /* cut[j]: the level at which j/nslots of a tile's time has passed.  Cost model of a level (profiles/r1_level_timing.txt):
+       above the first physics level 1/4, up to `ksplit` (the first latency-bound level) 0.58, below it 1. */
+    {
+      const int ktop = host_consts<T>(dev).ncldtop - 1;
+      double total = 0.0;
+      for (int k = 0; k < g.klev; ++k) total += k < ktop ? 0.25 : k < ksplit ? 0.58 : 1.0;
+      for (int j = 0; j < 16; ++j) sp.cut[j] = 0;
+      for (int j = 1; j < sp.nslots; ++j) {
+        const double want = total * j / sp.nslots;
+        double acc = 0.0;
+        int k = 0;
+        while (k < g.klev - 1 && acc < want) { acc += k < ktop ? 0.25 : k < ksplit ? 0.58 : 1.0; ++k; }
+        sp.cut[j] = k < 1 ? 1 : k;
+      }
+    }
+    sp.carry = ps.carry;
+    sp.ctl = ps.sm_b + kStaggerCtlOffset;
+    e = cudaMemsetAsync(sp.ctl, 0, (size_t)(2 + resident) * sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    StepConst<T> sc3;
+    fill_step<T>(host_consts<T>(dev), ptsphy, &sc3);
+    void *sargs[] = {(void *)&ft, (void *)&tm, (void *)&g, (void *)&sc3, (void *)&sp};
+    ++g_launches[KERNEL_TMAP];
+    return cudaLaunchKernel(sfn, dim3(resident), dim3(32), sargs, smem, stream);
+  }
   PersistPlan plan{ksplit, ntiles, ps.target_b > 0 ? ps.target_b : (per_sm[dev & 63][pi] * 7 + 6) / 12, ps.carry, ps.sm_b};
   StepConst<T> sc;
   fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
