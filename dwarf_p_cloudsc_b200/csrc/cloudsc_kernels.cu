@@ -1112,7 +1112,9 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
       int least = 0, greatest = 0;
       e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
       if (e != cudaSuccess) return e;
-      const int mid = greatest < least - 1 ? greatest + 1 : greatest;
+      int mid = greatest < least - 1 ? greatest + 1 : greatest;
+      /* $CLOUDSC_B200_STAGGER_PRIO=0 (measurement knob): three streams of equal priority, CTAs then go out in launch order */
+      if (const char *pe = getenv("CLOUDSC_B200_STAGGER_PRIO")) if (*pe == '0') greatest = mid = least;
       if ((e = cudaStreamCreateWithPriority(&ss.a, cudaStreamNonBlocking, greatest)) != cudaSuccess) return e;
       if ((e = cudaStreamCreateWithPriority(&ss.b, cudaStreamNonBlocking, mid)) != cudaSuccess) return e;
       if ((e = cudaStreamCreateWithPriority(&ss.c, cudaStreamNonBlocking, least)) != cudaSuccess) return e;
@@ -1149,21 +1151,24 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     ga.col_end = g.col_begin + npieces * 32;
     LaunchGeom gb = g;                                   /* whole tiles: the rest */
     gb.col_begin = ga.col_end;
+    /* $CLOUDSC_B200_STAGGER_PARTS (measurement knob, results then incomplete): bit 0 = A, bit 1 = B, bit 2 = C */
+    int parts = 7;
+    if (const char *pe = getenv("CLOUDSC_B200_STAGGER_PARTS")) parts = atoi(pe);
     if ((e = cudaEventRecord(ss.fork, stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(ss.a, ss.fork, 0)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(ss.b, ss.fork, 0)) != cudaSuccess) return e;
     pp.remainder = 0;
-    {
+    if (parts & 1) {
       void *args[] = {(void *)&ft, (void *)&tm, (void *)&ga, (void *)&sc3, (void *)&pp};
       ++g_launches[KERNEL_TMAP];
       if ((e = cudaLaunchKernel(pfn, dim3(npieces), dim3(32), args, smem, ss.a)) != cudaSuccess) return e;
     }
     if ((e = cudaEventRecord(ss.a_done, ss.a)) != cudaSuccess) return e;
-    if ((e = launch_sweep_tmap_t<T>(ft, tm, gb, ptsphy, ss.b)) != cudaSuccess) return e;
+    if (parts & 2) if ((e = launch_sweep_tmap_t<T>(ft, tm, gb, ptsphy, ss.b)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ss.b_done, ss.b)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(ss.c, ss.a_done, 0)) != cudaSuccess) return e;
     pp.remainder = 1;
-    {
+    if (parts & 4) {
       void *args[] = {(void *)&ft, (void *)&tm, (void *)&ga, (void *)&sc3, (void *)&pp};
       ++g_launches[KERNEL_TMAP];
       if ((e = cudaLaunchKernel(pfn, dim3(npieces), dim3(32), args, smem, ss.c)) != cudaSuccess) return e;
