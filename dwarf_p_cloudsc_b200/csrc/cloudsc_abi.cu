@@ -751,15 +751,30 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
      The kernel is ~2.5 % of a chunk's copy time: chunks are sized for overlap, not for kernel occupancy; the floor
      only avoids degenerate launches. */
   std::vector<int> sizes;
+  /* Every chunk starts on a block index that puts the host side of all its copies on a 4 KB boundary (one NPROMA row of
+     doubles is 1 KB at NPROMA 128: multiples of 4 blocks).  Copies that start inside a page cost 6 % of the PCIe rate
+     (tools/ubench/pcie.cu --pattern 2 --knobs 2, profiles/r2_pcie_pattern.txt).  $CLOUDSC_B200_E2E_ALIGN=0 turns it off. */
+  int ab = 1;
+  {
+    const char *al_env = getenv("CLOUDSC_B200_E2E_ALIGN");
+    if (!(al_env && *al_env == '0')) {
+      size_t rowbytes = (size_t)nproma * (precision == CLOUDSC_B200_FP32 ? 4 : 8), gcd = 4096, t = rowbytes % 4096;
+      while (t) { const size_t r = gcd % t; gcd = t; t = r; }
+      ab = (int)(4096 / gcd);
+      if (ab > 64) ab = 1;   /* odd NPROMA: no sensible alignment */
+    }
+  }
+  auto round_ab = [&](int n) { return n <= ab ? ab : (n + ab / 2) / ab * ab; };
   if (chunk_blocks <= 0) {
     chunk_blocks = (nblocks + nstreams * 6 - 1) / (nstreams * 6);
     const int min_blocks = (4096 + nproma - 1) / nproma;
     if (chunk_blocks < min_blocks) chunk_blocks = min_blocks;
+    chunk_blocks = round_ab(chunk_blocks);
     if (chunk_blocks > nblocks) chunk_blocks = nblocks;
     int left = nblocks;
     /* quarter- and half-size chunks at both ends: the first upload and the last download overlap with nothing
        (measured 3.7 + 2.3 ms of a 110 ms call with full-size end chunks, profiles/r2_e2e_trace.txt) */
-    const int q = chunk_blocks / 4, h = chunk_blocks / 2;
+    const int q = round_ab(chunk_blocks / 4), h = round_ab(chunk_blocks / 2);
     const int ramp_floor = (1024 + nproma - 1) / nproma;
     if (q >= ramp_floor && left > 4 * chunk_blocks) {
       sizes.push_back(q); sizes.push_back(h);

@@ -475,12 +475,40 @@ CLOUDSC_FN double mx0_fast(double x) {
 #endif
 }
 CLOUDSC_FN float mx0_fast(float x) { return mx(x, 0.0f); }
+/* min(x, C) / max(x, C) for a constant C > 0 whose low word is zero (1.0, 0.5, 160.0): x < C exactly when the high word of x
+ * is below that of C as a signed integer (negative x included), so the compare moves to the integer pipe as well. */
+template <int HI> CLOUDSC_FN double mn_hi(double x, double cval) {
+#if defined(__CUDACC__) && CLOUDSC_MX0_INT
+  return __double2hiint(x) < HI ? x : cval;
+#else
+  return x < cval ? x : cval;
+#endif
+}
+template <int HI> CLOUDSC_FN float mn_hi(float x, float cval) { return mn(x, cval); }
+template <int HI> CLOUDSC_FN double mx_hi(double x, double cval) {
+#if defined(__CUDACC__) && CLOUDSC_MX0_INT
+  return __double2hiint(x) < HI ? cval : x;
+#else
+  return x > cval ? x : cval;
+#endif
+}
+template <int HI> CLOUDSC_FN float mx_hi(float x, float cval) { return mx(x, cval); }
 #if CLOUDSC_STRICT
 #define CLOUDSC_MX0(x) mx((x), zero)
 #define CLOUDSC_MX0R(x) mx(zero, (x))
+#define CLOUDSC_MN1(x) mn((x), T(1.0))
+#define CLOUDSC_MN1R(x) mn(T(1.0), (x))
+#define CLOUDSC_MNH(x) mn((x), T(0.5))
+#define CLOUDSC_MNHR(x) mn(T(0.5), (x))
+#define CLOUDSC_MX160(x) mx((x), T(160.0))
 #else
 #define CLOUDSC_MX0(x) mx0_fast(x)
 #define CLOUDSC_MX0R(x) mx0_fast(x)
+#define CLOUDSC_MN1(x) mn_hi<0x3ff00000>((x), T(1.0))
+#define CLOUDSC_MN1R(x) mn_hi<0x3ff00000>((x), T(1.0))
+#define CLOUDSC_MNH(x) mn_hi<0x3fe00000>((x), T(0.5))
+#define CLOUDSC_MNHR(x) mn_hi<0x3fe00000>((x), T(0.5))
+#define CLOUDSC_MX160(x) mx_hi<0x40640000>((x), T(160.0))
 #endif
 #if CLOUDSC_STRICT
 #define CLOUDSC_RCP(x) (one / (x))
@@ -581,7 +609,7 @@ struct Carry {
 template <typename T>
 CLOUDSC_FN T foealfa(const CloudscConst<T> &c, T t) {
   const T x = (mx(c.rtice, mn(c.rtwat, t)) - c.rtice) * c.rtwat_rtice_r;
-  return mn(T(1.0), x * x);
+  return CLOUDSC_MN1R(x * x);
 }
 template <typename T>
 CLOUDSC_FN T foeldcpm(const CloudscConst<T> &c, T al) { return al * c.ralvdcp + (T(1.0) - al) * c.ralsdcp; }
@@ -596,7 +624,7 @@ CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
   const T el = ex(CLOUDSC_DIVR(c.r3les * (tn - c.rtt), dl, rdl));
   const T ei = ex(CLOUDSC_DIVR(c.r3ies * (tn - c.rtt), di, rdi));
   T qsat = (c.r2es * (al * el + (one - al) * ei)) * qp;
-  qsat = mn(T(0.5), qsat);
+  qsat = CLOUDSC_MNHR(qsat);
 #if CLOUDSC_STRICT
   const T cor = one / (one - c.retv * qsat);
   qsat = qsat * cor;
@@ -638,7 +666,7 @@ CLOUDSC_FN void deposition_prep(const CloudscConst<T> &c, const T ptsphy, const 
   ice0 = mx(icecld, (icenuclei * c.riceinit) * r_rho);
 #endif
   inew = CLOUDSC_POW15((c.p0666 * cvds) * ptsphy + CLOUDSC_POW(ice0, c.p0666));
-  infactor = mn(CLOUDSC_DIVR(icenuclei, T(15000.0), c.r_15000), one);
+  infactor = CLOUDSC_MN1(CLOUDSC_DIVR(icenuclei, T(15000.0), c.r_15000));
 }
 
 /* CLOUDSC_DEPOS_EARLY (experiment): evaluate deposition_prep() next to the Newton steps of 3.4 -- both are long dependent
@@ -902,7 +930,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
     /* ---- FOEALFA of this level (:588; also needed by the flux section at every level) */
     const T alfa_w = foealfa(c, t);
     /* ---- cloud fraction in [0,1], :625 */
-    a = CLOUDSC_MX0R(mn(one, a));
+    a = CLOUDSC_MX0R(CLOUDSC_MN1R(a));
 
     /* values of this level the flux section needs (zqxn2d stays 0 above ncldtop, :503) */
     T qxn2d[4] = {zero, zero, zero, zero};
@@ -920,12 +948,12 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T r_pap = CLOUDSC_RCP(pap);
       const T e_liq = ex(CLOUDSC_DIVR(c.r3les * (t - c.rtt), dl, r_dl));
       const T e_ice = ex(CLOUDSC_DIVR(c.r3ies * (t - c.rtt), di, r_di));
-      const T foeewmt = mn(CLOUDSC_DIVR(c.r2es * (alfa_w * e_liq + (one - alfa_w) * e_ice), pap, r_pap), T(0.5));
+      const T foeewmt = CLOUDSC_MNH(CLOUDSC_DIVR(c.r2es * (alfa_w * e_liq + (one - alfa_w) * e_ice), pap, r_pap));
       const T cor_m = CLOUDSC_RCP(one - c.retv * foeewmt);
       const T qsmix = CLOUDSC_DIVR(foeewmt, one - c.retv * foeewmt, cor_m);
       const T zalfa = CLOUDSC_MX0R(cs(one, t - c.rtt));
       /* (the reference applies min(0.5, .) twice here; the second one is the identity) */
-      const T foeew = mn(CLOUDSC_DIVR(zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice), pap, r_pap), T(0.5));
+      const T foeew = CLOUDSC_MNH(CLOUDSC_DIVR(zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice), pap, r_pap));
       const T cor_i = CLOUDSC_RCP(one - c.retv * foeew);
       const T qsice = CLOUDSC_DIVR(foeew, one - c.retv * foeew, cor_i);
       /* zqsliq (:607-609) is only read by the rain-evaporation block and is evaluated there */
@@ -1031,7 +1059,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         const T dtdiab = mn(dpmxdt * dtdp, mx(-dpmxdt * dtdp, zzzdt)) * ptsphy; /* + ralfdcp*zldefr, zldefr == 0 */
         const T dtforc = (dtdp * wtot) * ptsphy + dtdiab;
         T tn = t + dtforc;
-        tn = mx(tn, T(160.0));
+        tn = CLOUDSC_MX160(tn);
         T qsm = qsmix;
 #if CLOUDSC_DEPOS_EARLY && !CLOUDSC_STRICT
 #if CLOUDSC_DEPOS_EARLY == 1
@@ -1204,7 +1232,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         const T inew = dep_inew, ice0 = dep_ice0, infactor = dep_infactor;
         T depos = CLOUDSC_MX0(a * (inew - ice0));
         depos = mn(depos, qxfg[0]);
-        depos = depos * mn(infactor + (one - infactor) * (c.rdepliqrefrate + CLOUDSC_DIVR(s.cldtopdist, c.rdepliqrefdepth, c.r_rdepliqrefdepth)), one);
+        depos = depos * CLOUDSC_MN1(infactor + (one - infactor) * (c.rdepliqrefrate + CLOUDSC_DIVR(s.cldtopdist, c.rdepliqrefdepth, c.r_rdepliqrefdepth)));
         a01 = a01 + depos;
         qxfg[1] = qxfg[1] + depos; qxfg[0] = qxfg[0] - depos;
       }
@@ -1288,7 +1316,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           const T fallcorr = CLOUDSC_POW(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
           T snowrime = ((((c.p03 * s.covptot) * ptsphy) * c.rcl_const7s) * fallcorr) *
                        CLOUDSC_POW((rho * snowcld) * c.rcl_const1s, c.rcl_const8s);
-          snowrime = mn(snowrime, one);
+          snowrime = CLOUDSC_MN1(snowrime);
           qb03 = qb03 + snowrime;
         }
       }
@@ -1350,13 +1378,13 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* 4.5 evaporation of rain, Abel & Boutle, :1984-2038 */
       /* zzrh0 is shared by the rain and snow branches, :1990-1991 == :2051-2052 */
       T zzrh0 = c.rprecrhmax + CLOUDSC_DIVR(sc.one_m_rprecrhmax * s.covpmax, mx(c.zepsec, one_m_a), r_1ma);
-      zzrh0 = mn(mx(zzrh0, c.rprecrhmax), one);
+      zzrh0 = CLOUDSC_MN1(mx(zzrh0, c.rprecrhmax));
       {
         const T zzrh = mn(c.p08, zzrh0);
         bool rain_evap = covpclr > c.zepsec && qxfg[2] > c.zepsec;
         T qsliq = zero, qe = zero;
         if (CLOUDSC_RARE(rain_evap)) {
-          const T foeeliqt = mn(CLOUDSC_DIVR(c.r2es * e_liq, pap, r_pap), T(0.5));   /* :607-609 */
+          const T foeeliqt = CLOUDSC_MNH(CLOUDSC_DIVR(c.r2es * e_liq, pap, r_pap));   /* :607-609 */
           const T cor_l = CLOUDSC_RCP(one - c.retv * foeeliqt);
           (void)cor_l;
           qsliq = CLOUDSC_DIVR(foeeliqt, one - c.retv * foeeliqt, cor_l);
@@ -1407,7 +1435,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
 
       /* ================= 5.1 solver for cloud cover, :2168-2180 =========================== */
       T anew = CLOUDSC_DIV(a + solac, one + solab);
-      anew = mn(anew, one);
+      anew = CLOUDSC_MN1(anew);
       if (anew < c.ramin) anew = zero;
       T aorig_e = aorig;
       if constexpr (kReload) aorig_e = io.template ld<IN_PA>(k) + ptsphy * io.template ld<IN_TA>(k);

@@ -1163,9 +1163,10 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
       ++g_launches[KERNEL_TMAP];
       if ((e = cudaLaunchKernel(pfn, dim3(npieces), dim3(32), args, smem, ss.a)) != cudaSuccess) return e;
     }
-    if ((e = cudaEventRecord(ss.a_done, ss.a)) != cudaSuccess) return e;
+    /* (B is enqueued before anything that has to wait for A: where streams share a hardware queue, an event record behind A
+       would hold back everything enqueued after it until A has finished) */
     if (parts & 2) if ((e = launch_sweep_tmap_t<T>(ft, tm, gb, ptsphy, ss.b)) != cudaSuccess) return e;
-    if ((e = cudaEventRecord(ss.b_done, ss.b)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ss.a_done, ss.a)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(ss.c, ss.a_done, 0)) != cudaSuccess) return e;
     pp.remainder = 1;
     if (parts & 4) {
@@ -1173,6 +1174,7 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
       ++g_launches[KERNEL_TMAP];
       if ((e = cudaLaunchKernel(pfn, dim3(npieces), dim3(32), args, smem, ss.c)) != cudaSuccess) return e;
     }
+    if ((e = cudaEventRecord(ss.b_done, ss.b)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ss.c_done, ss.c)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(stream, ss.b_done, 0)) != cudaSuccess) return e;
     return cudaStreamWaitEvent(stream, ss.c_done, 0);
