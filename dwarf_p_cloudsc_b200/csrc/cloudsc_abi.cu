@@ -490,21 +490,18 @@ int cloudsc_b200_destroy(cloudsc_b200_state *st) {
  *   mode 2  streaming: 12 persistent warps per SM taking tiles from a queue, the input ring kept full across tiles
  *   mode 1  persistent: 12 warps per SM, each running its tiles in two pieces (levels [0, ksplit) and [ksplit, klev))
  *           and choosing the next piece so that about target_b of the SM's warps are in a lower piece at any time
- *   mode 3  staggered streaming: mode 2, but the first tile of slot j of an SM is only swept down to the level where
- *           j/nslots of a tile's time has passed (target_b = nslots, <= 0: all resident warps); the remainders are the
- *           last phase of the launch, longest first -- the SM's warps are spread over the sweep from the first cycle
  * ksplit <= 0 -> 3*klev/5; target_b <= 0 -> 7 of 12.  Results are bit-identical in every mode.
  */
 int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b) {
   if (!st) return fail(CLOUDSC_B200_EARG, "set_schedule: NULL state");
-  if (mode < 0 || mode > 3) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
+  if (mode < 0 || mode > 2) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
   if (ksplit >= st->klev) return fail(CLOUDSC_B200_EARG, "set_schedule: ksplit must be below klev");
   if (int rc = state_on_current_device(st, "set_schedule")) return rc;
   if (mode >= 1 && st->has_tm && !st->sched.carry) {
     const int ntiles = (st->nblocks * st->nproma + 31) / 32;
     CU(cudaMalloc(&st->sched.carry, persist_carry_bytes(ntiles, st->precision)));
-    CU(cudaMalloc((void **)&st->sched.sm_b, kSchedInts * sizeof(int)));
-    CU(cudaMemset(st->sched.sm_b, 0, kSchedInts * sizeof(int)));
+    CU(cudaMalloc((void **)&st->sched.sm_b, 1024 * sizeof(int)));
+    CU(cudaMemset(st->sched.sm_b, 0, 1024 * sizeof(int)));
     st->sched.carry_tiles = ntiles;
   }
   st->sched_mode = mode;
@@ -746,10 +743,12 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
   const int nblocks = (ngptot + nproma - 1) / nproma;
   if (nstreams <= 0) nstreams = 4;
   if (nstreams > kMaxLanes) nstreams = kMaxLanes;
-  /* chunk schedule.  Default: ~6 chunks per lane, so that pipeline fill (first upload) and drain (last download)
-     stay small against the transfer time, with half- and quarter-size chunks at both ends, which halves them again.
-     The kernel is ~2.5 % of a chunk's copy time: chunks are sized for overlap, not for kernel occupancy; the floor
-     only avoids degenerate launches. */
+  /* chunk schedule.  Default: ~5 chunks per lane, so that pipeline fill (first upload) and drain (last download)
+     stay small against the transfer time.  The kernel is ~2.5 % of a chunk's copy time: chunks are sized for overlap,
+     not for kernel occupancy; the floor only avoids degenerate launches.  Measured on one box, alternating
+     (tools/gpu_e2e_align.py, profiles/r2_e2e_align.txt): 20 equal chunks of 64 blocks 108.5 ms, 23 of 56 110.0 ms, 56 with
+     half- and quarter-size chunks at both ends ($CLOUDSC_B200_E2E_RAMP=1, the earlier default) 112.0 ms -- every chunk
+     costs its 50 copies, and the small ones at the ends cost more than the fill / drain time they save. */
   std::vector<int> sizes;
   /* Every chunk starts on a block index that puts the host side of all its copies on a 4 KB boundary (one NPROMA row of
      doubles is 1 KB at NPROMA 128: multiples of 4 blocks).  Copies that start inside a page cost 6 % of the PCIe rate
@@ -766,7 +765,7 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
   }
   auto round_ab = [&](int n) { return n <= ab ? ab : (n + ab / 2) / ab * ab; };
   if (chunk_blocks <= 0) {
-    chunk_blocks = (nblocks + nstreams * 6 - 1) / (nstreams * 6);
+    chunk_blocks = (nblocks + nstreams * 5 - 1) / (nstreams * 5);
     const int min_blocks = (4096 + nproma - 1) / nproma;
     if (chunk_blocks < min_blocks) chunk_blocks = min_blocks;
     chunk_blocks = round_ab(chunk_blocks);
@@ -776,7 +775,8 @@ int cloudsc_b200_run_host_ex(void *const host[CLOUDSC_NFIELDS], int ngptot, int 
        (measured 3.7 + 2.3 ms of a 110 ms call with full-size end chunks, profiles/r2_e2e_trace.txt) */
     const int q = round_ab(chunk_blocks / 4), h = round_ab(chunk_blocks / 2);
     const int ramp_floor = (1024 + nproma - 1) / nproma;
-    if (q >= ramp_floor && left > 4 * chunk_blocks) {
+    const char *ramp_env = getenv("CLOUDSC_B200_E2E_RAMP");
+    if (ramp_env && *ramp_env == '1' && q >= ramp_floor && left > 4 * chunk_blocks) {
       sizes.push_back(q); sizes.push_back(h);
       left -= q + h;
       const int tail = q + h;

@@ -645,69 +645,6 @@ cloudsc_sweep_stream(const __grid_constant__ FieldTable ft, const __grid_constan
   }
 }
 
-/* ---- staggered launch: the warps of an SM spread over the sweep from the first cycle on ------------------------------ */
-/*
- * Schedule mode 3.  With one CTA per tile every resident warp starts a tile at level 0 at the same moment, so the 12 warps of
- * an SM walk through the bandwidth-bound upper levels and then through the latency-bound cloudy levels together; the launch
- * list shows what that costs: a 1-wave launch takes 0.69 ms, every further wave 0.64 / 0.62 / 0.60 ms as the warps drift
- * apart, 0.58 ms in the steady state of a 12-wave launch (profiles/r2_wave_sizes.txt).  Mode 3 spreads them from the start
- * WITHOUT idling, with the hardware block scheduler doing the work -- three kernels on three streams of falling priority:
- *   A (highest)  `cloudsc_sweep_piece`, one CTA per piece: the first (nslots - 1) * per tiles of the launch, tile i only down
- *                to level cut[1 + i / per] -- a piece that takes about j/nslots of a tile; with per = number of SMs and CTAs
- *                dealt round-robin over the SMs every SM gets one piece of every length.  The state at the cut (the same
- *                `Carry` + parked slots as mode 1) is parked in `carry`.
- *   B (middle)   `cloudsc_sweep_tmap`, one CTA per whole tile, all the other tiles: its CTAs take the slots the pieces free,
- *                one by one -- from then on the SM's warps are 1/nslots of a tile apart.
- *   C (lowest)   `cloudsc_sweep_piece` again, after A: the remainders [cut, klev), longest first.  Lower priority than B,
- *                so they run when B has no CTA left to place: the launch ends on pieces of 11/12 ... 1/12 of a tile
- *                instead of whole tiles.
- * Bit-identical to mode 0 (the cut sweep is: tests/test_cpu_oracle.py::test_cut_sweep_is_bit_identical).
- */
-struct PiecePlan {
-  int per;         /* pieces per slot (= number of SMs) */
-  int remainder;   /* 0: levels [0, cut) and park the state; 1: levels [cut, klev) from the parked state */
-  int cut[16];     /* cut[j], j = 1 .. nslots - 1 */
-  void *carry;     /* [pieces][kCarryVals][32] elements */
-};
-
-template <typename T>
-__global__ void __launch_bounds__(32, warps_per_sm<T>())
-cloudsc_sweep_piece(const __grid_constant__ FieldTable ft, const __grid_constant__ TensorMaps tm, const LaunchGeom g,
-                    const __grid_constant__ StepConst<T> sc, const __grid_constant__ PiecePlan plan) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  using IO = TmapIO<T, true>;
-  const int tile = (int)blockIdx.x;
-  const int cut = plan.cut[1 + tile / plan.per];
-  const int kb = plan.remainder ? cut : 0, ke = plan.remainder ? g.klev : cut;
-  const int ccol = g.col_begin + tile * IO::kCols;
-  if (ccol >= g.col_end) return;
-  const int ibl = ccol / g.nproma;
-  const int jl0 = ccol - ibl * g.nproma;
-  const int jl = jl0 + (int)threadIdx.x;
-  const long long bL = (long long)ibl * g.klev * g.nproma, bH = (long long)ibl * (g.klev + 1) * g.nproma;
-  const unsigned rows = (unsigned)kb * (unsigned)g.nproma;   /* output offsets start at the piece's first level */
-  const unsigned bar0 = smem_u32(smem_raw + 2 * IO::kStage);
-  IO io{ft, tm, ibl, jl0, g.nproma, g.klev, dev_consts<T>().ncldtop - 2,
-        smem_u32(smem_raw), bar0,
-        reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
-        bH + jl, (long long)ibl * g.nproma + jl,
-        (unsigned)(bL + jl) + rows, (unsigned)(bH + jl + g.nproma) + rows, (unsigned)(bL * 5 + jl) + rows, (unsigned)(g.klev * g.nproma),
-        ccol + (int)threadIdx.x < g.col_end, kb, ke, -kb,
-        static_cast<T *>(plan.carry) + (size_t)tile * (kCarryVals * 32) + threadIdx.x, -1, 0};
-  if (threadIdx.x == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
-    mbar_fence_init();
-  }
-  __syncwarp();
-  if (elect_one()) {
-    io.issue(kb);
-    if (kb + 1 < ke) io.issue(kb + 1);
-  }
-  __syncwarp();
-  cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
-}
-
 /* ---- IO policy 3: thread-private cp.async ring, pre-offset slot pointers, streaming stores -------- */
 /*
  * Every thread stages ITS OWN column: per level 27 `cp.async` (SASS LDGSTS, 8 bytes each, a warp
@@ -1041,14 +978,6 @@ cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const 
 }
 
 /* persistent kernel: grid = the resident set (SMs x warps per SM), never more than the tiles */
-/* mode 3: three streams of falling priority per device, created on first use (kept for the life of the process) */
-struct StaggerStreams {
-  cudaStream_t a, b, c;
-  cudaEvent_t fork, a_done, b_done, c_done;
-  bool ready;
-};
-static StaggerStreams g_stagger[64];
-
 template <typename T>
 static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
                                           const PersistSchedule &ps, cudaStream_t stream) {
@@ -1101,84 +1030,6 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
   int ksplit = ps.ksplit > 0 ? ps.ksplit : (3 * g.klev) / 5;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > g.klev - 1) ksplit = g.klev - 1;
-  if (ps.mode == 3) {
-    const void *pfn = (const void *)cloudsc_sweep_piece<T>;
-    e = cudaFuncSetAttribute(pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(pfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    StaggerStreams &ss = g_stagger[dev & 63];
-    if (!ss.ready) {
-      int least = 0, greatest = 0;
-      e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
-      if (e != cudaSuccess) return e;
-      int mid = greatest < least - 1 ? greatest + 1 : greatest;
-      /* $CLOUDSC_B200_STAGGER_PRIO=0 (measurement knob): three streams of equal priority, CTAs then go out in launch order */
-      if (const char *pe = getenv("CLOUDSC_B200_STAGGER_PRIO")) if (*pe == '0') greatest = mid = least;
-      if ((e = cudaStreamCreateWithPriority(&ss.a, cudaStreamNonBlocking, greatest)) != cudaSuccess) return e;
-      if ((e = cudaStreamCreateWithPriority(&ss.b, cudaStreamNonBlocking, mid)) != cudaSuccess) return e;
-      if ((e = cudaStreamCreateWithPriority(&ss.c, cudaStreamNonBlocking, least)) != cudaSuccess) return e;
-      for (cudaEvent_t *ev : {&ss.fork, &ss.a_done, &ss.b_done, &ss.c_done})
-        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
-      ss.ready = true;
-    }
-    PiecePlan pp;
-    int nslots = ps.target_b > 0 ? ps.target_b : per_sm[dev & 63][pi];
-    if (nslots > 16) nslots = 16;
-    if (nslots < 2) return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
-    pp.per = sms[dev & 63];
-    /* cut[j]: the level at which j/nslots of a tile's time has passed.  Cost model of a level (profiles/r1_level_timing.txt):
-       above the first physics level 1/4, up to `ksplit` (the first latency-bound level) 0.58, below it 1. */
-    {
-      const int ktop = host_consts<T>(dev).ncldtop - 1;
-      double total = 0.0;
-      for (int k = 0; k < g.klev; ++k) total += k < ktop ? 0.25 : k < ksplit ? 0.58 : 1.0;
-      for (int j = 0; j < 16; ++j) pp.cut[j] = 1;
-      for (int j = 1; j < nslots; ++j) {
-        const double want = total * j / nslots;
-        double acc = 0.0;
-        int k = 0;
-        while (k < g.klev - 1 && acc < want) { acc += k < ktop ? 0.25 : k < ksplit ? 0.58 : 1.0; ++k; }
-        pp.cut[j] = k < 1 ? 1 : k;
-      }
-    }
-    pp.carry = ps.carry;
-    const int npieces = (nslots - 1) * pp.per;
-    if (npieces > ps.carry_tiles || npieces >= ntiles) return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
-    StepConst<T> sc3;
-    fill_step<T>(host_consts<T>(dev), ptsphy, &sc3);
-    LaunchGeom ga = g;                                   /* pieces: the first npieces tiles */
-    ga.col_end = g.col_begin + npieces * 32;
-    LaunchGeom gb = g;                                   /* whole tiles: the rest */
-    gb.col_begin = ga.col_end;
-    /* $CLOUDSC_B200_STAGGER_PARTS (measurement knob, results then incomplete): bit 0 = A, bit 1 = B, bit 2 = C */
-    int parts = 7;
-    if (const char *pe = getenv("CLOUDSC_B200_STAGGER_PARTS")) parts = atoi(pe);
-    if ((e = cudaEventRecord(ss.fork, stream)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(ss.a, ss.fork, 0)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(ss.b, ss.fork, 0)) != cudaSuccess) return e;
-    pp.remainder = 0;
-    if (parts & 1) {
-      void *args[] = {(void *)&ft, (void *)&tm, (void *)&ga, (void *)&sc3, (void *)&pp};
-      ++g_launches[KERNEL_TMAP];
-      if ((e = cudaLaunchKernel(pfn, dim3(npieces), dim3(32), args, smem, ss.a)) != cudaSuccess) return e;
-    }
-    /* (B is enqueued before anything that has to wait for A: where streams share a hardware queue, an event record behind A
-       would hold back everything enqueued after it until A has finished) */
-    if (parts & 2) if ((e = launch_sweep_tmap_t<T>(ft, tm, gb, ptsphy, ss.b)) != cudaSuccess) return e;
-    if ((e = cudaEventRecord(ss.a_done, ss.a)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(ss.c, ss.a_done, 0)) != cudaSuccess) return e;
-    pp.remainder = 1;
-    if (parts & 4) {
-      void *args[] = {(void *)&ft, (void *)&tm, (void *)&ga, (void *)&sc3, (void *)&pp};
-      ++g_launches[KERNEL_TMAP];
-      if ((e = cudaLaunchKernel(pfn, dim3(npieces), dim3(32), args, smem, ss.c)) != cudaSuccess) return e;
-    }
-    if ((e = cudaEventRecord(ss.b_done, ss.b)) != cudaSuccess) return e;
-    if ((e = cudaEventRecord(ss.c_done, ss.c)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(stream, ss.b_done, 0)) != cudaSuccess) return e;
-    return cudaStreamWaitEvent(stream, ss.c_done, 0);
-  }
   PersistPlan plan{ksplit, ntiles, ps.target_b > 0 ? ps.target_b : (per_sm[dev & 63][pi] * 7 + 6) / 12, ps.carry, ps.sm_b};
   StepConst<T> sc;
   fill_step<T>(host_consts<T>(dev), ptsphy, &sc);

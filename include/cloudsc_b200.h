@@ -175,11 +175,7 @@ int cloudsc_b200_download(cloudsc_b200_state *st, void *const host_fields[CLOUDS
 int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, int nblocks, void *stream);
 /* how step() schedules the 32-column tiles of a launch: mode 0 = one CTA per tile; mode 1 = persistent warps that run
  * the upper (bandwidth-bound) and lower (latency-bound) parts of their tiles interleaved, cut at level `ksplit`, with
- * about `target_b` of an SM's 12 warps in a lower part at any time (<= 0: defaults); mode 2 = persistent warps taking
- * whole tiles from a queue; mode 3 = mode 2 with the warps of an SM spread over the sweep from the start: the first tile of
- * slot j of `target_b` slots (<= 0: the resident warps per SM) is cut where j/target_b of a tile's time has passed (`ksplit`
- * = first latency-bound level of the cost model, <= 0: 3/5 klev) and its remainder runs in the last phase of the launch.
- * Bit-identical results in every mode. */
+ * about `target_b` of an SM's 12 warps in a lower part at any time (<= 0: defaults).  Bit-identical results. */
 int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b);
 /* restore PLUDE from the pristine copy kept at upload() (the kernel scales it in place) */
 int cloudsc_b200_reset_inout(cloudsc_b200_state *st, void *stream);
