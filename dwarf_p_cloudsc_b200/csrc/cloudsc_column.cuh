@@ -496,17 +496,6 @@ CLOUDSC_FN double mx0_fast(double x) {
 #endif
 }
 CLOUDSC_FN float mx0_fast(float x) { return mx(x, 0.0f); }
-/* Sign of a difference d = x - y as an integer (> 0, == 0, < 0 as d is): on the device the high word of d.  x - y is zero
- * only for x == y and then +0, and a non-zero difference of two temperatures (~ 200 .. 330 K) is >= 2^-45: its high word is
- * non-zero.  The ~12 tests of t against rtt / rthomo per level then cost one ISETP each instead of one DSETP. */
-CLOUDSC_FN int sign_hi(double d) {
-#if defined(__CUDACC__) && CLOUDSC_MX0_INT
-  return __double2hiint(d);
-#else
-  return d > 0.0 ? 1 : d < 0.0 ? -1 : 0;
-#endif
-}
-CLOUDSC_FN int sign_hi(float d) { return d > 0.0f ? 1 : d < 0.0f ? -1 : 0; }
 /* min(x, C) / max(x, C) for a constant C > 0 whose low word is zero (1.0, 0.5, 160.0): x < C exactly when the high word of x
  * is below that of C as a signed integer (negative x included), so the compare moves to the integer pipe as well. */
 template <int HI> CLOUDSC_FN double mn_hi(double x, double cval) {
@@ -985,8 +974,6 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
     if (k >= ktop) {
       /* ================= saturation values of this level, :583-640 ======================== */
       /* (the reference computes them for all levels; above ncldtop only zfoealfa is ever read) */
-      /* t relative to the triple point and to the homogeneous-freezing threshold, as signs (sign_hi above) */
-      const int t_rtt = sign_hi(t - c.rtt), t_homo = sign_hi(t - c.rthomo);
       const T dl = t - c.r4les, di = t - c.r4ies;
       const T r_dl = CLOUDSC_RCP(dl), r_di = CLOUDSC_RCP(di);
       const T r_pap = CLOUDSC_RCP(pap);
@@ -995,7 +982,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       const T foeewmt = CLOUDSC_MNH(CLOUDSC_DIVR(c.r2es * (alfa_w * e_liq + (one - alfa_w) * e_ice), pap, r_pap));
       const T cor_m = CLOUDSC_RCP(one - c.retv * foeewmt);
       const T qsmix = CLOUDSC_DIVR(foeewmt, one - c.retv * foeewmt, cor_m);
-      const T zalfa = t_rtt >= 0 ? one : zero;   /* max(0, sign(1, t - rtt)), :596 */
+      const T zalfa = CLOUDSC_MX0R(cs(one, t - c.rtt));
       /* (the reference applies min(0.5, .) twice here; the second one is the identity) */
       const T foeew = CLOUDSC_MNH(CLOUDSC_DIVR(zalfa * (c.r2es * e_liq) + (one - zalfa) * (c.r2es * e_ice), pap, r_pap));
       const T cor_i = CLOUDSC_RCP(one - c.retv * foeew);
@@ -1083,7 +1070,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       } else {
         qe_nc = qv + li;
       }
-      const T fac_nc = (c.nssopt == 0 || t_rtt >= 0) ? one : fokoop;
+      const T fac_nc = (c.nssopt == 0 || t >= c.rtt) ? one : fokoop;
       const bool new_cloud_window = a < sc.one_m_zepsec && qe_nc >= qsice * fac_nc * rhc && qe_nc < qsice * fac_nc;
       const bool need_dqs = (a > zero) | new_cloud_window;
       /* ================= 3.4 condensation/evaporation due to dqsat/dT, :1137-1182 ========= */
@@ -1107,7 +1094,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         T qsm = qsmix;
 #if CLOUDSC_DEPOS_EARLY && !CLOUDSC_STRICT
 #if CLOUDSC_DEPOS_EARLY == 1
-        if (qx[0] > c.rlmin && t_rtt < 0)
+        if (qx[0] > c.rlmin && t < c.rtt)
 #endif
         { /* (== 2: for every lane that is here, without a branch -- the values are only read where 3.7 applies) */
           deposition_prep<T>(c, ptsphy, t, pap, rho, r_rho, r_t, e_ice, fokoop, icecld, dep_inew, dep_ice0, dep_infactor);
@@ -1125,7 +1112,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       /* ================= 3.1 ice supersaturation adjustment, :879-952 ===================== */
       {
         T fac, facI;
-        if (c.nssopt == 0 || t_rtt >= 0) { fac = one; facI = one; }
+        if (c.nssopt == 0 || t >= c.rtt) { fac = one; facI = one; }
         else { fac = a + fokoop * one_m_a; facI = sc.faci_koop; }
         T supsat;
         if (a > sc.one_m_ramin) {
@@ -1135,13 +1122,13 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           supsat = CLOUDSC_MX0(CLOUDSC_DIVR(one_m_a * (qp1env - fac * qsice), corqsice, r_corqsice));
         }
         if (CLOUDSC_RARE(supsat > c.zepsec)) {
-          if (t_homo > 0) { a04 = a04 - supsat; qxfg[0] = qxfg[0] + supsat; }
+          if (t > c.rthomo) { a04 = a04 - supsat; qxfg[0] = qxfg[0] + supsat; }
           else              { a14 = a14 - supsat; qxfg[1] = qxfg[1] + supsat; }
           solac = one_m_a * facI;
         }
         const T psupsat = io.template ld<IN_PSUPSAT>(k);
         if (CLOUDSC_RARE(psupsat > c.zepsec)) {
-          if (t_homo > 0) { d0 = d0 + psupsat; psupsrce0 = psupsat; qxfg[0] = qxfg[0] + psupsat; }
+          if (t > c.rthomo) { d0 = d0 + psupsat; psupsrce0 = psupsat; qxfg[0] = qxfg[0] + psupsat; }
           else              { d1 = d1 + psupsat; psupsrce1 = psupsat; qxfg[1] = qxfg[1] + psupsat; }
           solac = one_m_a * facI;
         }
@@ -1238,7 +1225,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         lcond1 = CLOUDSC_MX0(mn(lcond1, cdmax));
         lcond1 = a * lcond1;
         if (lcond1 < c.rlmin) lcond1 = zero;
-        if (t_homo > 0) { a04 = a04 - lcond1; qxfg[0] = qxfg[0] + lcond1; }
+        if (t > c.rthomo) { a04 = a04 - lcond1; qxfg[0] = qxfg[0] + lcond1; }
         else              { a14 = a14 - lcond1; qxfg[1] = qxfg[1] + lcond1; }
       }
       /* 3.4b (2) generation of new clouds, :1254-1361 */
@@ -1257,7 +1244,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
           if (one_m_a < c.zepsec || lcond2 < c.rlmin) { lcond2 = zero; acond = zero; }
           if (lcond2 == zero) acond = zero;
           solac = solac + acond;
-          if (t_homo > 0) { a04 = a04 - lcond2; qxfg[0] = qxfg[0] + lcond2; }
+          if (t > c.rthomo) { a04 = a04 - lcond2; qxfg[0] = qxfg[0] + lcond2; }
           else              { a14 = a14 - lcond2; qxfg[1] = qxfg[1] + lcond2; }
         }
       }
@@ -1271,7 +1258,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       else s.cldtopdist = s.cldtopdist + (dp * r_rho) * sc.zrg_r;
 #endif
       park_st<PARK_CLDTOPDIST>(io, s.cldtopdist, s.cldtopdist);
-      if (qxfg[0] > c.rlmin && t_rtt < 0) {
+      if (qxfg[0] > c.rlmin && t < c.rtt) {
         if (!dep_ready) deposition_prep<T>(c, ptsphy, t, pap, rho, r_rho, r_t, e_ice, fokoop, icecld, dep_inew, dep_ice0, dep_infactor);
         const T inew = dep_inew, ice0 = dep_ice0, infactor = dep_infactor;
         T depos = CLOUDSC_MX0(a * (inew - ice0));
@@ -1321,7 +1308,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       }
 
       /* 4.3a autoconversion to snow, :1617-1637 */
-      if (t_rtt <= 0) {
+      if (t <= c.rtt) {
         if (icecld > c.zepsec) {
           T zco = sc.snowlin * CLOUDSC_EXP_COLD(c.rsnowlin2 * (t - c.rtt));
           T x = CLOUDSC_DIVR(icecld, c.rlcritsnow, c.r_rlcritsnow);
@@ -1348,14 +1335,14 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
         } else {
           rainaut = zero; rainacc = zero;
         }
-        if (t_rtt <= 0) {
+        if (t <= c.rtt) {
           a03 = a03 + rainaut; a03 = a03 + rainacc;
         } else {
           a02 = a02 + rainaut; a02 = a02 + rainacc;
         }
       }
       /* riming of snow by cloud water, :1771-1785 */
-      if (t_rtt <= 0 && liqcld > c.zepsec) {
+      if (t <= c.rtt && liqcld > c.zepsec) {
         if (CLOUDSC_RARE(s.covptot > c.p001 && snowcld > c.zepsec)) {
           const T fallcorr = CLOUDSC_POW(CLOUDSC_DIVR(c.rdensref, rho, r_rho), c.p04);
           T snowrime = ((((c.p03 * s.covptot) * ptsphy) * c.rcl_const7s) * fallcorr) *
@@ -1369,7 +1356,7 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       {
         const T icetot = qxfg[1] + qxfg[3];
         T meltmax = zero;
-        if (CLOUDSC_RARE(icetot > c.zepsec && t_rtt > 0)) {
+        if (CLOUDSC_RARE(icetot > c.zepsec && t > c.rtt)) {
           const T subsat = CLOUDSC_MX0(qsice - qv);
           const T tdmtw0 = t - c.rtt - subsat * (c.ztw1 + c.ztw2 * (pap - ztw3) - c.ztw4 * (t - ztw5));
           const T cons1 = ab(CLOUDSC_DIVR(ptsphy * (one + T(0.5) * tdmtw0), c.rtaumel, c.r_rtaumel));
@@ -1390,11 +1377,11 @@ CLOUDSC_FN void cloudsc_column(const CloudscConst<T> &c, const StepConst<T> &sc,
       }
       /* 4.4b freezing of rain, :1866-1906 */
       if (CLOUDSC_RARE(qx[2] > c.zepsec)) {
-        if (t_rtt <= 0 && s.tp1_m1 > c.rtt) {
+        if (t <= c.rtt && s.tp1_m1 > c.rtt) {
           const T qpre = mx(qx[3] + qx[2], c.zepsec);
           park_st<PARK_RAINFRAC>(io, s.rainfrac, CLOUDSC_DIV(qx[2], qpre));
         }
-        if (t_rtt < 0) {
+        if (t < c.rtt) {
           T frzmax;
           if (park_ld<PARK_RAINFRAC>(io, s.rainfrac) > c.p08) {
             const T lambda = CLOUDSC_POW(CLOUDSC_DIV(c.rcl_fac1, rho * qx[2]), c.rcl_fac2);
