@@ -73,6 +73,8 @@ lib.cloudsc_b200_host_alloc_ex.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctyp
 lib.cloudsc_b200_host_alloc_ex.restype = _i
 lib.cloudsc_b200_host_free.argtypes = [_vp]
 lib.cloudsc_b200_host_free.restype = _i
+lib.cloudsc_b200_selftest_primitives.argtypes = [_vp, _i, _vp, _vp]
+lib.cloudsc_b200_selftest_primitives.restype = _i
 lib.cloudsc_b200_launch_counts.argtypes = [ctypes.POINTER(ctypes.c_longlong * 5)]
 for _n in ("set_params", "launch", "kernel_info", "launch_counts", "run_host", "run_host_ex", "release_thread", "release_cache", "create", "destroy", "upload", "download",
            "step", "reset_inout", "sync", "set_variant", "get_variant", "device_count",
@@ -148,6 +150,17 @@ def run_host(host_fields: Mapping[str, object], ngptot: int, nproma: int, klev: 
 
 
 KERNEL_FAMILIES = ("tmap", "tile", "direct", "pipe", "direct_aer")
+
+
+def selftest_primitives(x):
+    """The fast-mode primitives of the kernels evaluated on the device for every element of the CUDA double tensor `x`
+    (cloudsc_b200_selftest_primitives): returns a [n, 8] tensor."""
+    import torch
+    assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+    out = torch.empty((x.numel(), 8), dtype=torch.float64, device=x.device)
+    _check(lib.cloudsc_b200_selftest_primitives(ctypes.c_void_p(x.data_ptr()), x.numel(), ctypes.c_void_p(out.data_ptr()),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
 
 
 def launch_counts() -> Dict[str, int]:

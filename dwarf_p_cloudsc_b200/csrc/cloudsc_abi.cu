@@ -416,6 +416,12 @@ int cloudsc_b200_launch(void *const dev_fields[CLOUDSC_NFIELDS], int ngptot, int
 
 /* kernels launched by this process since the library was loaded, per family:
    {tensor-map TMA, bulk-copy TMA, plain loads, cp.async ring, plain loads with aerosol inputs} */
+int cloudsc_b200_selftest_primitives(const double *x, int n, double *out, void *stream) {
+  if (n < 0 || (n > 0 && (!x || !out))) return fail(CLOUDSC_B200_EARG, "selftest_primitives: bad arguments");
+  CU(launch_selftest_primitives(x, n, out, (cudaStream_t)stream));
+  return 0;
+}
+
 int cloudsc_b200_launch_counts(long long out[5]) {
   if (!out) return fail(CLOUDSC_B200_EARG, "launch_counts: out is NULL");
   static_assert(KERNEL_FAMILIES == 5, "update cloudsc_b200_launch_counts");

@@ -1070,6 +1070,32 @@ cudaError_t tmap_kernel_info(int precision, int out[8]) {
   return precision == CLOUDSC_B200_FP32 ? tmap_kernel_info_t<float>(out) : tmap_kernel_info_t<double>(out);
 }
 
+/* ---- self-test of the fast-mode primitives (cloudsc_b200_selftest_primitives) ---------------------------------------- */
+__global__ void selftest_primitives_kernel(const double *x, int n, double *out) {
+  exp2_tab_init();
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  const double v = x[i];
+  const double zero = 0.0;
+  (void)zero;
+  typedef double T;
+  double *o = out + 8 * (size_t)i;
+  o[0] = CLOUDSC_MX0(v);
+  o[1] = CLOUDSC_MN1(v);
+  o[2] = CLOUDSC_MNH(v);
+  o[3] = CLOUDSC_MX160(v);
+  /* the clamp of exp_fast_lo, observable through exp: exp(-700) for everything below */
+  o[4] = exp_fast_lo(v > 700.0 ? 700.0 : v);
+  o[5] = exp_fast(v > 700.0 ? 700.0 : v < -700.0 ? -700.0 : v);
+  o[6] = v != 0.0 ? log_fast(v < 0.0 ? -v : v) : 0.0;
+  o[7] = v != 0.0 ? rcp_fast(v) : 0.0;
+}
+cudaError_t launch_selftest_primitives(const double *x, int n, double *out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  selftest_primitives_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, n, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,
                          cudaStream_t stream) {
   if (g.col_end <= g.col_begin) return cudaSuccess;

@@ -78,6 +78,7 @@ cudaError_t launch_sweep_persist(const FieldTable &ft, const TensorMaps &tm, con
 size_t persist_carry_bytes(int ntiles, int precision);
 cudaError_t tmap_kernel_info(int precision, int out[8]);
 
+cudaError_t launch_selftest_primitives(const double *x, int n, double *out, cudaStream_t stream);
 cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<float> &c32);
 cudaError_t launch_sweep(const FieldTable &ft, const LaunchGeom &g, double ptsphy, int precision, int variant,
                          cudaStream_t stream);

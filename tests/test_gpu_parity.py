@@ -846,3 +846,45 @@ def test_library_host_buffers(built, oracle, input_data, flags):
         H.clear()
         for hb in bufs:
             hb.free()
+
+
+def test_integer_pipe_compares_are_exact(built):
+    """The product kernels evaluate max(x,0), min(x,1), min(x,0.5), max(x,160) and the max(x,-700) in front of every pow as
+    tests on the HIGH WORD of x (one ISETP instead of a DSETP on the FP64 pipe: cloudsc_column.cuh mx0_fast / mn_hi / mx_hi /
+    exp_fast_lo).  That is exact for every non-NaN x because the constants have a zero low word; checked here bit for bit
+    (value for value: zeros of either sign compare equal) on zeros, denormals, infinities, the neighbours of every
+    threshold and 200 000 random bit patterns.  The same call pins exp / log / reciprocal of the fast mode against
+    numpy: 2e-15 relative (exp, 1/x) and 3e-16 absolute-or-relative (log)."""
+    import torch
+    from dwarf_p_cloudsc_b200 import api
+    rng = np.random.default_rng(7)
+    special = [0.0, -0.0, 5e-324, -5e-324, 2.2250738585072014e-308, -2.2250738585072014e-308, np.inf, -np.inf, 1e308, -1e308]
+    for c in (0.0, 0.5, 1.0, 160.0, -700.0, 700.0):
+        x = c
+        for _ in range(3):
+            special += [x]
+            x = np.nextafter(x, np.inf)
+        x = c
+        for _ in range(3):
+            x = np.nextafter(x, -np.inf)
+            special += [x]
+    bits = rng.integers(0, 2**64, size=200000, dtype=np.uint64)
+    rnd = bits.view(np.float64)
+    rnd = rnd[np.isfinite(rnd)]
+    moderate = np.concatenate([rng.uniform(-800, 800, 50000), rng.uniform(-2, 2, 50000), 10.0 ** rng.uniform(-300, 300, 20000)])
+    x = np.concatenate([np.array(special), rnd, moderate])
+    out = api.selftest_primitives(torch.from_numpy(x).cuda()).cpu().numpy()
+    with np.errstate(all="ignore"):
+        assert np.array_equal(out[:, 0], np.where(x > 0.0, x, 0.0))
+        assert np.array_equal(out[:, 1], np.where(x < 1.0, x, 1.0))
+        assert np.array_equal(out[:, 2], np.where(x < 0.5, x, 0.5))
+        assert np.array_equal(out[:, 3], np.where(x > 160.0, x, 160.0))
+        xe = np.clip(x, -700.0, 700.0)
+        ref = np.exp(xe)
+        assert np.all(np.abs(out[:, 4] - ref) <= 2e-15 * ref), "exp_fast_lo: the clamp at -700 or exp itself"
+        assert np.all(np.abs(out[:, 5] - ref) <= 2e-15 * ref)
+        nz = (x != 0.0) & (np.abs(x) >= 2.2250738585072014e-308) & np.isfinite(x)
+        lref = np.log(np.abs(x[nz]))
+        assert np.all(np.abs(out[nz, 6] - lref) <= 3e-16 * np.maximum(1.0, np.abs(lref)))
+        inv = nz & (np.abs(x) > 1e-300) & (np.abs(x) < 1e300)
+        assert np.all(np.abs(out[inv, 7] * x[inv] - 1.0) <= 2e-15)
