@@ -759,9 +759,9 @@ def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma,
     interleaved, the state at the cut going through a device buffer (launches big enough for the persistent path:
     >= 2 tiles per resident warp; incl. a ragged last tile).  Any cut level and any mix target gives the SAME bits
     (the schedule never enters the arithmetic; the CPU proof that a cut sweep equals the uncut one is
-    test_cut_sweep_is_bit_identical) and, on the shipped data, the bits of the one-CTA-per-tile kernel.  On synthetic
-    inputs that reach the warm-phase code the two kernels differ by rounding (4e-16: the compiler contracts multiply-adds
-    differently in the two instantiations), so there the bar is the FP64 parity tolerance."""
+    test_cut_sweep_is_bit_identical) and, on the shipped data, the bits of the one-CTA-per-tile kernel and of the streaming
+    kernel.  On synthetic inputs that reach the warm-phase code different kernels differ by rounding (4e-16: the compiler
+    contracts multiply-adds per kernel), so between kernels the bar there is 1e-14 on the dwarf's error table."""
     from dwarf_p_cloudsc_b200 import params, state, api, validate
     cols, scalars, klon, klev = input_data
     p, k = params.params_from_scalars(scalars)
@@ -786,11 +786,14 @@ def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma,
         st.close()
     for n in outs:
         assert np.array_equal(res[1][n], res[2][n]), n      # any cut, any mix: same bits (and the per-SM counters returned to zero)
-        assert np.array_equal(res[1][n], res[3][n]), n      # streaming tile queue (mode 2): same instantiation of the column code
         if not perturbation:
+            assert np.array_equal(res[1][n], res[3][n]), n  # streaming tile queue (mode 2)
             assert np.array_equal(res[0][n], res[1][n]), n
-    errs = validate.validate(res[1], res[0], ngptot)
-    assert validate.all_pass(errs) and max(e.rel_l1 for e in errs) < 1e-14, "\n" + validate.format_table(errs)
+    # different kernels (one CTA per tile / persistent / streaming): same bits on the shipped data, rounding-level differences
+    # where the warm-phase code runs (the compiler contracts multiply-adds per kernel)
+    for other in (res[0], res[3]):
+        errs = validate.validate(res[1], other, ngptot)
+        assert validate.all_pass(errs) and max(e.rel_l1 for e in errs) < 1e-14, "\n" + validate.format_table(errs)
 
 
 def test_c_driver_power_sampling(built):
