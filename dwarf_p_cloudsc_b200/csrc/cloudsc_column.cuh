@@ -292,6 +292,24 @@ CLOUDSC_FN float rcp_fast(float x) {
   return 1.0f / x;
 #endif
 }
+/* a / b where the reciprocal itself is not needed again: the quotient a r0 is refined directly, q = q0 + q0 (e + e^2) with
+ * q0 = a r0 evaluated NEXT TO e = 1 - b r0 -- three dependent FP64 operations behind the MUFU seed instead of four */
+#ifndef CLOUDSC_DIV_FUSED
+#define CLOUDSC_DIV_FUSED 1
+#endif
+CLOUDSC_FN double div_fast(double a, double b) {
+#if defined(__CUDACC__) && CLOUDSC_DIV_FUSED
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  const double e = fma(-b, r, 1.0);
+  const double q0 = a * r;
+  const double p = fma(e, e, e);
+  return fma(q0, p, q0);
+#else
+  return a * rcp_fast(b);
+#endif
+}
+CLOUDSC_FN float div_fast(float a, float b) { return a * rcp_fast(b); }
 
 /*
  * log(x) for normal positive x: x = m 2^e with m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1),
@@ -319,16 +337,16 @@ CLOUDSC_FN double log_fast(double x) {
   xb = ((long long)hi << 32) | (long long)(unsigned)lo;
   std::memcpy(&m, &xb, 8);
 #endif
-  const double s = (m - 1.0) * rcp_fast(m + 1.0);
+  const double s = div_fast(m - 1.0, m + 1.0);
   const double z = s * s;
   const double z2 = z * z;
   const double g01 = 0.19999999999949722 * z + 0.3333333333333335;
   const double g23 = 0.11111105565129939 * z + 0.14285714313001635;
   const double g45 = 0.07665855309105386 * z + 0.09091444727837474;
   const double g46 = 0.07308292712444311 * z2 + g45;
+  const double fe = (double)e;
   const double g = (g46 * z2 + g23) * z2 + g01;
   const double lm = (s * z) * g + s;           /* atanh s */
-  const double fe = (double)e;
   return fe * 6.93147180369123816490e-01 + (fe * 1.90821492927058770002e-10 + (lm + lm));
 }
 /*
@@ -458,8 +476,20 @@ CLOUDSC_FN float pow_fast(float x, float y) {
 #endif
 }
 /* sqrt(x) for normal x > 0: MUFU.RSQ64H seed, two Newton steps on 1/sqrt, one on the root */
+#ifndef CLOUDSC_SQRT_CUBIC
+#define CLOUDSC_SQRT_CUBIC 1
+#endif
 CLOUDSC_FN double sqrt_fast(double x) {
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && CLOUDSC_SQRT_CUBIC
+  /* one cubically convergent step on the root itself: t = x y0 ~ sqrt x, eps = 1 - x y0^2 (~2^-20 for the MUFU.RSQ64H seed),
+     sqrt x = t (1 - eps)^(-1/2) = t (1 + eps/2 + 3 eps^2 / 8 + O(eps^3 ~ 2^-60)): four dependent operations instead of nine */
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = x * y;
+  const double eps = fma(-t, y, 1.0);
+  const double p = fma(eps, 0.375, 0.5);
+  return fma(t * eps, p, t);
+#elif defined(__CUDACC__)
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   const double h = 0.5 * x;
@@ -547,7 +577,7 @@ template <typename T> CLOUDSC_FN T ex(T x) { return ex_lib(x); }
 template <typename T> CLOUDSC_FN T ex_lo(T x) { return ex_lib(x); }
 #else
 #define CLOUDSC_RCP(x) rcp_fast(x)
-#define CLOUDSC_DIV(a, b) ((a) * rcp_fast(b))
+#define CLOUDSC_DIV(a, b) div_fast((a), (b))
 #define CLOUDSC_DIVR(a, b, r) ((a) * (r))
 /* CLOUDSC_CALLS: the FP64 pow (log + exp, ~62 instructions, 13 sites) and the exp of the process blocks as ONE
  * out-of-line copy each.  The loop body of the FP64 kernel (2400 hot instructions = 38 KB) does not fit the SM's
@@ -666,7 +696,7 @@ CLOUDSC_FN void satadj_step(const CloudscConst<T> &c, T qp, T &tn, T &qsm) {
      one reciprocal on the Newton step's critical path instead of two */
   const T dem = (al * c.r5alvcp) * (rdl * rdl) + ((one - al) * c.r5alscp) * (rdi * rdi);
   const T d = one - c.retv * qsat;
-  const T cond = ((qsm * d - qsat) * d) * rcp_fast(d * d + qsat * dem);
+  const T cond = div_fast((qsm * d - qsat) * d, d * d + qsat * dem);
 #endif
   tn = tn + foeldcpm(c, al) * cond;
   qsm = qsm - cond;
@@ -692,8 +722,8 @@ CLOUDSC_FN void deposition_prep(const CloudscConst<T> &c, const T ptsphy, const 
   ice0 = mx(icecld, (icenuclei * c.riceinit) / rho);
 #else
   const T add = (c.rlstt * ((c.rlstt * c.r_rv) * r_t - one)) * (c.r_p0024 * r_t);
-  const T bdd = ((c.rv * t) * pap) * rcp_fast(c.p221 * vpice);
-  const T cvds = ((c.p78 * CLOUDSC_POW(icenuclei * r_rho, c.p0666)) * (vpliq - vpice)) * rcp_fast((c.p887 * (add + bdd)) * vpice);
+  const T bdd = div_fast((c.rv * t) * pap, c.p221 * vpice);
+  const T cvds = div_fast((c.p78 * CLOUDSC_POW(icenuclei * r_rho, c.p0666)) * (vpliq - vpice), (c.p887 * (add + bdd)) * vpice);
   ice0 = mx(icecld, (icenuclei * c.riceinit) * r_rho);
 #endif
   inew = CLOUDSC_POW15((c.p0666 * cvds) * ptsphy + CLOUDSC_POW(ice0, c.p0666));

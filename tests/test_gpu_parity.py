@@ -857,7 +857,7 @@ def test_integer_pipe_compares_are_exact(built):
     exp_fast_lo).  That is exact for every non-NaN x because the constants have a zero low word; checked here bit for bit
     (value for value: zeros of either sign compare equal) on zeros, denormals, infinities, the neighbours of every
     threshold and 200 000 random bit patterns.  The same call pins exp / log / reciprocal of the fast mode against
-    numpy: 2e-15 relative (exp, 1/x) and 3e-16 absolute-or-relative (log)."""
+    numpy: 2e-15 relative (exp, 1/x, a/x), 1e-15 (sqrt) and 3e-16 absolute-or-relative (log)."""
     import torch
     from dwarf_p_cloudsc_b200 import api
     rng = np.random.default_rng(7)
@@ -891,3 +891,6 @@ def test_integer_pipe_compares_are_exact(built):
         assert np.all(np.abs(out[nz, 6] - lref) <= 3e-16 * np.maximum(1.0, np.abs(lref)))
         inv = nz & (np.abs(x) > 1e-300) & (np.abs(x) < 1e300)
         assert np.all(np.abs(out[inv, 7] * x[inv] - 1.0) <= 2e-15)
+        sref = np.sqrt(np.abs(x[inv]))
+        assert np.all(np.abs(out[inv, 8] - sref) <= 1e-15 * sref), "sqrt_fast: one cubic step on the MUFU.RSQ64H seed"
+        assert np.all(np.abs(out[inv, 9] * x[inv] / 1.2345678901234567 - 1.0) <= 2e-15), "div_fast: quotient refined directly"
