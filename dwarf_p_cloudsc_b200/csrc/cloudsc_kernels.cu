@@ -1079,7 +1079,7 @@ __global__ void selftest_primitives_kernel(const double *x, int n, double *out) 
   const double zero = 0.0;
   (void)zero;
   typedef double T;
-  double *o = out + 10 * (size_t)i;
+  double *o = out + 14 * (size_t)i;
   o[0] = CLOUDSC_MX0(v);
   o[1] = CLOUDSC_MN1(v);
   o[2] = CLOUDSC_MNH(v);
@@ -1091,6 +1091,17 @@ __global__ void selftest_primitives_kernel(const double *x, int n, double *out) 
   o[7] = v != 0.0 ? rcp_fast(v) : 0.0;
   o[8] = v != 0.0 ? sqrt_fast(v < 0.0 ? -v : v) : 0.0;
   o[9] = v != 0.0 ? div_fast(1.2345678901234567, v) : 0.0;
+  {
+    const double av = v < 0.0 ? -v : v;
+    o[10] = pow_fast(av, 0.666);
+    o[11] = pow_fast(av, 2.47);
+#if CLOUDSC_EXP_TABLE
+    o[12] = pow_mufu(av, 0.666);
+    o[13] = pow_mufu(av, 2.47);
+#else
+    o[12] = o[10]; o[13] = o[11];
+#endif
+  }
 }
 cudaError_t launch_selftest_primitives(const double *x, int n, double *out, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
