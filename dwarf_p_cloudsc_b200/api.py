@@ -154,10 +154,10 @@ KERNEL_FAMILIES = ("tmap", "tile", "direct", "pipe", "direct_aer")
 
 def selftest_primitives(x):
     """The fast-mode primitives of the kernels evaluated on the device for every element of the CUDA double tensor `x`
-    (cloudsc_b200_selftest_primitives): returns a [n, 14] tensor."""
+    (cloudsc_b200_selftest_primitives): returns a [n, 12] tensor."""
     import torch
     assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
-    out = torch.empty((x.numel(), 14), dtype=torch.float64, device=x.device)
+    out = torch.empty((x.numel(), 12), dtype=torch.float64, device=x.device)
     _check(lib.cloudsc_b200_selftest_primitives(ctypes.c_void_p(x.data_ptr()), x.numel(), ctypes.c_void_p(out.data_ptr()),
                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return out

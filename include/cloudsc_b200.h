@@ -134,10 +134,10 @@ int cloudsc_b200_kernel_info(int nproma, int precision, int out[8]);
  * out[0] tensor-map TMA kernel, [1] bulk-copy TMA kernel, [2] plain-load kernel, [3] cp.async-ring kernel,
  * [4] plain-load kernel with the aerosol inputs (laericesed / laericeauto) */
 int cloudsc_b200_launch_counts(long long out[5]);
-/* Self-test of the arithmetic primitives of the product kernels on the current device: for each of the n inputs, out[14 i + ..] =
+/* Self-test of the arithmetic primitives of the product kernels on the current device: for each of the n inputs, out[12 i + ..] =
  * { max(x,0), min(x,1), min(x,0.5), max(x,160), max(x,-700) as the kernels evaluate them (high-word integer tests),
  *   exp_fast(clamp(x, -700, 700)), log_fast(|x|), rcp_fast(x), sqrt_fast(|x|), div_fast(1.2345678901234567, x) (x != 0),
- *   pow_fast(|x|, 0.666), pow_fast(|x|, 2.47), and the same two through pow_mufu }.  Device pointers.  tests/ check the first five
+ *   pow_fast(|x|, 0.666), pow_fast(|x|, 2.47) }.  Device pointers.  tests/ check the first five
  * bit for bit against the plain compares on zeros of both signs, denormals and the neighbours of every threshold. */
 int cloudsc_b200_selftest_primitives(const double *x, int n, double *out, void *stream);
 

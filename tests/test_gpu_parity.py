@@ -894,13 +894,12 @@ def test_integer_pipe_compares_are_exact(built):
         sref = np.sqrt(np.abs(x[inv]))
         assert np.all(np.abs(out[inv, 8] - sref) <= 1e-15 * sref), "sqrt_fast: one cubic step on the MUFU.RSQ64H seed"
         assert np.all(np.abs(out[inv, 9] * x[inv] / 1.2345678901234567 - 1.0) <= 2e-15), "div_fast: quotient refined directly"
-        # x^y: exp(y log x) (pow_fast) and the MUFU.LG2-seeded form (pow_mufu): |y ln x| * 3e-16 + 1e-15 relative; x = 0 and
-        # results below 1e-300 only have to be tiny (the exponent is clamped at -700 / -1010 log2 units)
+        # x^y = exp(y log x): |y ln x| * 3e-16 + 1e-15 relative; x = 0 only has to come out tiny (log 0 ~ -709, the exponent of
+        # the exp is clamped at -700)
         ax = np.abs(x)
-        for col, yy in ((10, 0.666), (11, 2.47), (12, 0.666), (13, 2.47)):
+        for col, yy in ((10, 0.666), (11, 2.47)):
             pref = ax ** yy
             ok = np.isfinite(pref) & (pref > 1e-290) & (pref < 1e290) & (ax >= 2.2250738585072014e-308)
             bar = (np.abs(yy * np.log(ax[ok])) * 3e-16 + 1e-15) * pref[ok]
             assert np.all(np.abs(out[ok, col] - pref[ok]) <= bar), (col, yy)
-            tiny = pref < 1e-300
-            assert np.all(out[tiny, col] <= 1e-280), (col, yy)
+            assert np.all(out[ax == 0.0, col] <= 1e-200), (col, yy)
