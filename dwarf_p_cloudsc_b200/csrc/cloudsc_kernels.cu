@@ -470,6 +470,12 @@ struct TmapIO {
 #endif
 template <typename T> constexpr int warps_per_sm() { return sizeof(T) == 4 ? 16 : CLOUDSC_F64_WARPS_PER_SM; }
 
+__device__ __forceinline__ unsigned smid_of_cta() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(32, warps_per_sm<T>())
 cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant__ TensorMaps tm, const LaunchGeom g,
@@ -499,7 +505,21 @@ cloudsc_sweep_tmap(const __grid_constant__ FieldTable ft, const __grid_constant_
     if (g.klev > 1) io.issue(1);
   }
   __syncwarp();
+  /* -DCLOUDSC_TILE_TIMES (tools/gpu_tile_times.py): start / end (%globaltimer, ns) and SM of every tile into the TENDENCY_CML_T
+     buffer, which the kernel never touches otherwise */
+#ifdef CLOUDSC_TILE_TIMES
+  long long tt0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
+#endif
   cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+#ifdef CLOUDSC_TILE_TIMES
+  if (threadIdx.x == 0 && ft.p[CLOUDSC_F_TENDENCY_CML_T]) {
+    long long tt1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt1));
+    long long *d = static_cast<long long *>(ft.p[CLOUDSC_F_TENDENCY_CML_T]) + 3 * (size_t)blockIdx.x;
+    d[0] = tt0; d[1] = tt1; d[2] = (long long)smid_of_cta();
+  }
+#endif
 }
 
 /* ---- persistent kernel: every warp walks its own column tiles, upper and lower parts interleaved ------------------- */

@@ -16,8 +16,8 @@ dbg = torch.zeros(10 * 4 * klev, dtype=torch.int64, device="cuda")
 # the state never allocates TENDENCY_CML_T (use N): point its table entry at the debug buffer
 from dwarf_p_cloudsc_b200.params import FIELD_INDEX
 tab_ptr = ctypes.cast(st._h, ctypes.POINTER(ctypes.c_void_p))
-# struct cloudsc_b200_state { int x6; void *dev[56]; ... }: dev[] starts at byte 24
-dev = ctypes.cast(st._h.value + 24, ctypes.POINTER(ctypes.c_void_p * 56)).contents
+# struct cloudsc_b200_state { int x7; void *dev[56]; ... }: dev[] starts at byte 32
+dev = ctypes.cast(st._h.value + 32, ctypes.POINTER(ctypes.c_void_p * 56)).contents
 dev[FIELD_INDEX["TENDENCY_CML_T"]] = dbg.data_ptr()
 for it in range(3):
     st.reset_inout(); dbg.zero_()
