@@ -500,14 +500,14 @@ int cloudsc_b200_destroy(cloudsc_b200_state *st) {
  */
 int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b) {
   if (!st) return fail(CLOUDSC_B200_EARG, "set_schedule: NULL state");
-  if (mode < 0 || mode > 2) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
+  if (mode < 0 || mode > 3) return fail(CLOUDSC_B200_EARG, "set_schedule: unknown mode %d", mode);
   if (ksplit >= st->klev) return fail(CLOUDSC_B200_EARG, "set_schedule: ksplit must be below klev");
   if (int rc = state_on_current_device(st, "set_schedule")) return rc;
   if (mode >= 1 && st->has_tm && !st->sched.carry) {
     const int ntiles = (st->nblocks * st->nproma + 31) / 32;
     CU(cudaMalloc(&st->sched.carry, persist_carry_bytes(ntiles, st->precision)));
-    CU(cudaMalloc((void **)&st->sched.sm_b, 1024 * sizeof(int)));
-    CU(cudaMemset(st->sched.sm_b, 0, 1024 * sizeof(int)));
+    CU(cudaMalloc((void **)&st->sched.sm_b, kSchedInts * sizeof(int)));
+    CU(cudaMemset(st->sched.sm_b, 0, kSchedInts * sizeof(int)));
     st->sched.carry_tiles = ntiles;
   }
   st->sched_mode = mode;

@@ -665,6 +665,89 @@ cloudsc_sweep_stream(const __grid_constant__ FieldTable ft, const __grid_constan
   }
 }
 
+/* ---- split-tail launch: the last slots of a launch are filled with half tiles ------------------------------------------ */
+/*
+ * Schedule mode 3.  With one CTA per tile the launch ends on whole tiles of ~0.55 ms: in the last 150 us only 1 149 -> 171 of
+ * the 1 776 slots still hold one, 10 % of the launch (profiles/r2_tile_times.txt).  Here `nsplit` tiles are swept in two
+ * pieces by different CTAs of ONE launch, in block-index order (the order the hardware dispatches them in):
+ *   blocks [0, nsplit)                    levels [0, cut) of tile b; the state at the cut (`Carry` + parked slots, as mode 1)
+ *                                         goes to `carry`, then flag[b] = seq
+ *   blocks [nsplit, ntiles)               whole tiles
+ *   blocks [ntiles, ntiles + nsplit)      levels [cut, klev) of tile b - ntiles, after flag[..] == seq (set about two tile
+ *                                         times earlier: the wait is there for correctness, not for timing)
+ * so the pieces that fill the end of the launch are about half a tile long.  `seq` changes with every launch: no flag is
+ * ever reset.  Bit-identical to the other schedules of this instantiation (a cut sweep is: test_cut_sweep_is_bit_identical).
+ */
+struct SplitPlan {
+  int ntiles, nsplit, cut, seq;
+  void *carry;     /* [nsplit][kCarryVals][32] elements */
+  int *flag;       /* [nsplit] */
+};
+
+/* the upper piece of a tile ran about two tile times before its lower piece is dispatched; make sure, and see its parked state.
+ * (One opaque asm statement: written as a C++ loop -- inline or out of line -- the spin costs the sweep behind it 24 bytes of
+ * spills inside the level loop.) */
+__device__ __forceinline__ void split_wait(const int *flag, int seq) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .s32 v;\n"
+      "SPLIT_WAIT:\n"
+      "ld.acquire.gpu.global.s32 v, [%0];\n"
+      "setp.eq.s32 p, v, %1;\n"
+      "@p bra SPLIT_DONE;\n"
+      "nanosleep.u32 500;\n"
+      "bra SPLIT_WAIT;\n"
+      "SPLIT_DONE:\n"
+      "}\n" ::"l"(flag), "r"(seq) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32, warps_per_sm<T>())
+cloudsc_sweep_split(const __grid_constant__ FieldTable ft, const __grid_constant__ TensorMaps tm, const LaunchGeom g,
+                    const __grid_constant__ StepConst<T> sc, const __grid_constant__ SplitPlan plan) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using IO = TmapIO<T, true>;
+  const int b = (int)blockIdx.x;
+  const bool tail = b >= plan.ntiles;
+  const int tile = tail ? b - plan.ntiles : b;
+  const bool split = tile < plan.nsplit;
+  const int kb = tail ? plan.cut : 0, ke = (split && !tail) ? plan.cut : g.klev;
+  const int ccol = g.col_begin + tile * IO::kCols;
+  if (ccol >= g.col_end) return;
+  const int ibl = ccol / g.nproma;
+  const int jl0 = ccol - ibl * g.nproma;
+  const int jl = jl0 + (int)threadIdx.x;
+  const long long bL = (long long)ibl * g.klev * g.nproma, bH = (long long)ibl * (g.klev + 1) * g.nproma;
+  const unsigned rows = (unsigned)kb * (unsigned)g.nproma;   /* output offsets start at the piece's first level */
+  const unsigned bar0 = smem_u32(smem_raw + 2 * IO::kStage);
+  IO io{ft, tm, ibl, jl0, g.nproma, g.klev, dev_consts<T>().ncldtop - 2,
+        smem_u32(smem_raw), bar0,
+        reinterpret_cast<const T *>(smem_raw) + threadIdx.x, nullptr,
+        bH + jl, (long long)ibl * g.nproma + jl,
+        (unsigned)(bL + jl) + rows, (unsigned)(bH + jl + g.nproma) + rows, (unsigned)(bL * 5 + jl) + rows, (unsigned)(g.klev * g.nproma),
+        ccol + (int)threadIdx.x < g.col_end, kb, ke, -kb,
+        static_cast<T *>(plan.carry) + (size_t)(split ? tile : 0) * (kCarryVals * 32) + threadIdx.x, -1, 0};
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    mbar_fence_init();
+  }
+  if (tail) split_wait(&plan.flag[tile], plan.seq);   /* every lane polls: a wait under `lane == 0` is divergent control flow */
+  __syncwarp();
+  if (elect_one()) {
+    io.issue(kb);
+    if (kb + 1 < ke) io.issue(kb + 1);
+  }
+  __syncwarp();
+  cloudsc_column<T>(dev_consts<T>(), sc, io, g.klev);
+  if (io.ke < g.klev) {         /* an upper piece: blocks [0, nsplit), tile == block index */
+    __threadfence();            /* every lane: its part of the parked state is visible before the flag */
+    __syncwarp();
+    if (threadIdx.x == 0) atomicExch(&plan.flag[blockIdx.x], plan.seq);
+  }
+}
+
 /* ---- IO policy 3: thread-private cp.async ring, pre-offset slot pointers, streaming stores -------- */
 /*
  * Every thread stages ITS OWN column: per level 27 `cp.async` (SASS LDGSTS, 8 bytes each, a warp
@@ -1050,6 +1133,32 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
   int ksplit = ps.ksplit > 0 ? ps.ksplit : (3 * g.klev) / 5;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > g.klev - 1) ksplit = g.klev - 1;
+  if (ps.mode == 3) {
+    const void *sfn = (const void *)cloudsc_sweep_split<T>;
+    e = cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    static int seq[64];
+    int per = ps.target_b > 0 ? ps.target_b : per_sm[dev & 63][pi];       /* split tiles per SM */
+    if (per > per_sm[dev & 63][pi]) per = per_sm[dev & 63][pi];
+    SplitPlan sp;
+    sp.ntiles = ntiles;
+    sp.nsplit = per * sms[dev & 63];
+    if (sp.nsplit > kSplitFlags) sp.nsplit = kSplitFlags;
+    if (sp.nsplit > ps.carry_tiles) sp.nsplit = ps.carry_tiles;
+    if (sp.nsplit > ntiles) sp.nsplit = ntiles;
+    sp.cut = ksplit;
+    sp.seq = ++seq[dev & 63];
+    if (sp.seq == 0) sp.seq = ++seq[dev & 63];
+    sp.carry = ps.carry;
+    sp.flag = ps.sm_b + kSplitFlagOffset;
+    StepConst<T> sc3;
+    fill_step<T>(host_consts<T>(dev), ptsphy, &sc3);
+    void *sargs[] = {(void *)&ft, (void *)&tm, (void *)&g, (void *)&sc3, (void *)&sp};
+    ++g_launches[KERNEL_TMAP];
+    return cudaLaunchKernel(sfn, dim3(ntiles + sp.nsplit), dim3(32), sargs, smem, stream);
+  }
   PersistPlan plan{ksplit, ntiles, ps.target_b > 0 ? ps.target_b : (per_sm[dev & 63][pi] * 7 + 6) / 12, ps.carry, ps.sm_b};
   StepConst<T> sc;
   fill_step<T>(host_consts<T>(dev), ptsphy, &sc);

@@ -67,12 +67,16 @@ cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const 
 /* persistent variant of the tensor-map kernel (cloudsc_kernels.cu, "persistent kernel"); falls back to launch_sweep_tmap
  * for launches with fewer than two rounds of tiles per resident warp.  ksplit / target_b <= 0: defaults. */
 struct PersistSchedule {
-  int mode;         /* 1: interleaved upper / lower pieces (cloudsc_sweep_persist); 2: streaming tile queue (cloudsc_sweep_stream) */
+  int mode;         /* 1: interleaved upper / lower pieces (cloudsc_sweep_persist); 2: streaming tile queue (cloudsc_sweep_stream);
+                       3: split tail (cloudsc_sweep_split; ksplit = cut level, target_b = split tiles per SM) */
   int ksplit, target_b;
   void *carry;      /* persist_carry_bytes(carry_tiles, precision) bytes of device scratch */
   int carry_tiles;
-  int *sm_b;        /* >= 1024 zero-initialised ints of device memory */
+  int *sm_b;        /* >= kSchedInts zero-initialised ints of device memory */
 };
+/* layout of PersistSchedule::sm_b: [0, 512) per-SM counters of mode 1, [512] the tile queue of mode 2, [kSplitFlagOffset, +kSplitFlags)
+ * the "upper piece done" flags of mode 3 */
+constexpr int kSplitFlagOffset = 1024, kSplitFlags = 4096, kSchedInts = kSplitFlagOffset + kSplitFlags;
 cudaError_t launch_sweep_persist(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy, int precision,
                                  const PersistSchedule &ps, cudaStream_t stream);
 size_t persist_carry_bytes(int ntiles, int precision);

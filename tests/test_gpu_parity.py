@@ -754,9 +754,9 @@ def test_level0_link_of_the_reference_driver(built, args):
 @pytest.mark.parametrize("ngptot,nproma,perturbation,ksplit,target_b", [(163840, 128, "", 0, 0), (120000, 64, "warm+land+conv+rain+moist+tend", 40, 3),
                                                                         (131071, 32, "sparse+warm+conv", 136, 12), (114688, 128, "hot+rain+moist+conv", 1, 1)])
 def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma, perturbation, ksplit, target_b):
-    """cloudsc_b200_set_schedule(mode 1 / mode 2): persistent warps that take their tiles from a queue with the input
-    ring kept full across tiles (2), or that run the upper and lower parts of their column tiles
-    interleaved, the state at the cut going through a device buffer (launches big enough for the persistent path:
+    """cloudsc_b200_set_schedule(mode 1 / mode 2 / mode 3): persistent warps that take their tiles from a queue with the input
+    ring kept full across tiles (2), one launch whose last blocks are the lower halves of tiles split at a cut (3), or warps
+    that run the upper and lower parts of their column tiles interleaved, the state at the cut going through a device buffer (launches big enough for the persistent path:
     >= 2 tiles per resident warp; incl. a ragged last tile).  Any cut level and any mix target gives the SAME bits
     (the schedule never enters the arithmetic; the CPU proof that a cut sweep equals the uncut one is
     test_cut_sweep_is_bit_identical) and, on the shipped data, the bits of the one-CTA-per-tile kernel and of the streaming
@@ -773,7 +773,8 @@ def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma,
     try:
         st.upload(F)
         res = []
-        for mode, ks, tb in ((0, 0, 0), (1, ksplit, target_b), (1, max(1, klev - 1 - ksplit), 12 - min(target_b, 11)), (2, 0, 0)):
+        for mode, ks, tb in ((0, 0, 0), (1, ksplit, target_b), (1, max(1, klev - 1 - ksplit), 12 - min(target_b, 11)), (2, 0, 0),
+                             (3, ksplit, 0), (3, max(1, klev - 1 - ksplit), 5)):
             st.set_schedule(mode, ks, tb)
             st.reset_inout()
             c0 = api.launch_counts()
@@ -786,12 +787,14 @@ def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma,
         st.close()
     for n in outs:
         assert np.array_equal(res[1][n], res[2][n]), n      # any cut, any mix: same bits (and the per-SM counters returned to zero)
+        assert np.array_equal(res[4][n], res[5][n]), n      # split tail (mode 3): any cut, any number of split tiles
         if not perturbation:
             assert np.array_equal(res[1][n], res[3][n]), n  # streaming tile queue (mode 2)
+            assert np.array_equal(res[1][n], res[4][n]), n  # split tail (mode 3)
             assert np.array_equal(res[0][n], res[1][n]), n
     # different kernels (one CTA per tile / persistent / streaming): same bits on the shipped data, rounding-level differences
     # where the warm-phase code runs (the compiler contracts multiply-adds per kernel)
-    for other in (res[0], res[3]):
+    for other in (res[0], res[3], res[4]):
         errs = validate.validate(res[1], other, ngptot)
         assert validate.all_pass(errs) and max(e.rel_l1 for e in errs) < 1e-14, "\n" + validate.format_table(errs)
 
