@@ -331,13 +331,14 @@ def run_b200(args, rank, local_rank, world):
     st.upload(H, stream)
     torch.cuda.synchronize()
     kinfo = st.kernel_info()
+    sched = st.get_schedule()             # FP64 states default to the split-tail launch (mode 3) when the launch is big enough
 
     def restore():
         st.reset_inout(stream)          # PLUDE is in/out: pristine copy kept by upload()
 
     def step():
         st.step(pts, 0, 0, stream)
-    log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s; kernel {kinfo}")
+    log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s; kernel {kinfo}; schedule {sched}")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -382,6 +383,8 @@ def run_b200(args, rank, local_rank, world):
     ms = shard.reduce_max(ms, dist, dev)          # time = max over ranks; no collective on the data path
     gpu_launches = sum(launches1.values()) - sum(launches0.values())
     launched = {n: launches1[n] - launches0[n] for n in launches1 if launches1[n] != launches0[n]}
+    if "tmap" in launched:                # the counter is per kernel family; the schedule says which tensor-map kernel it was
+        launched[KERNEL_OF_SCHEDULE[sched["used"]]] = launched.pop("tmap")
 
     # -- correctness of what was just timed: EVERY column of EVERY rank against the replicated reference.h5, the
     #    per-rank norms combined as the reference's MPI mode combines them (validate_mod.F90:197-199: MIN/MAX/SUM)
@@ -452,13 +455,20 @@ def run_b200(args, rank, local_rank, world):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f)
-            traffic = (traffic.get("fp32") or {}).get("dram_bytes_per_launch") if fp32 else traffic.get("dram_bytes_per_launch")
+            kname = KERNEL_OF_SCHEDULE[sched["used"]]
+            if fp32:
+                traffic = (traffic.get("fp32") or {}).get("dram_bytes_per_launch")
+            elif kname in traffic.get("by_kernel", {}):
+                traffic = traffic["by_kernel"][kname]["dram_bytes_per_launch"]
+            else:                         # a capture of another kernel says nothing about this one
+                traffic = traffic.get("dram_bytes_per_launch") if traffic.get("kernel", kname) == kname else None
         if ngptot != 163840:
             traffic = None                # the ncu capture is of the default workload
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "cloudsc_sweep",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": KERNEL_OF_SCHEDULE[sched["used"]],
                 "algorithmic_bytes_per_column": bytes_col, "columns_per_launch": ngptot}
 
     cpu = None
@@ -486,11 +496,14 @@ def run_b200(args, rank, local_rank, world):
         "cpu_baseline": cpu, "gpu_reference": gpu_reference,
         "validated_vs_reference_h5": ok, "validated_columns": validated_columns, "validation_worst_l1": worst_l1,
         "device_api": "cloudsc_b200_create/upload/step (arena state)",
-        "step_ms": {"min": min(times_ms), "median": statistics.median(times_ms), "max": max(times_ms)}, "kernel_info": kinfo,
+        "step_ms": {"min": min(times_ms), "median": statistics.median(times_ms), "max": max(times_ms)}, "kernel_info": kinfo, "schedule": sched,
     }
     emit(line)
     if dist:
         dist.destroy_process_group()
+
+
+KERNEL_OF_SCHEDULE = {0: "cloudsc_sweep_tmap", 1: "cloudsc_sweep_persist", 2: "cloudsc_sweep_stream", 3: "cloudsc_sweep_split"}
 
 
 def main():

@@ -62,6 +62,8 @@ lib.cloudsc_b200_step.argtypes = [_vp, _d, _i, _i, _vp]
 lib.cloudsc_b200_reset_inout.argtypes = [_vp, _vp]
 lib.cloudsc_b200_set_schedule.argtypes = [_vp, _i, _i, _i]
 lib.cloudsc_b200_set_schedule.restype = _i
+lib.cloudsc_b200_get_schedule.argtypes = [_vp, ctypes.POINTER(ctypes.c_int * 4)]
+lib.cloudsc_b200_get_schedule.restype = _i
 lib.cloudsc_b200_field_ptr.restype = _vp
 lib.cloudsc_b200_field_ptr.argtypes = [_vp, _i]
 lib.cloudsc_b200_sync.argtypes = [_vp]
@@ -244,8 +246,18 @@ class State:
         _check(lib.cloudsc_b200_step(self._h, ptsphy, first_block, nblocks, ctypes.c_void_p(stream)))
 
     def set_schedule(self, mode: int, ksplit: int = 0, target_b: int = 0):
-        """0: one CTA per 32-column tile; 1: persistent warps, upper / lower parts of their tiles interleaved."""
+        """0: one CTA per 32-column tile; 1: persistent warps, upper / lower parts of their tiles interleaved; 2: persistent warps, tile
+        queue; 3: split tail (default of an FP64 state)."""
         _check(lib.cloudsc_b200_set_schedule(self._h, mode, ksplit, target_b))
+
+    SCHEDULE_NAMES = {0: "one CTA per tile", 1: "persistent, interleaved pieces", 2: "persistent, tile queue", 3: "split tail"}
+
+    def get_schedule(self) -> Dict[str, object]:
+        """The schedule as set and the one a step() over the whole state actually gets (`used`: small launches, aerosol runs
+        and states without tensor maps keep one CTA per tile)."""
+        out = (ctypes.c_int * 4)()
+        _check(lib.cloudsc_b200_get_schedule(self._h, ctypes.byref(out)))
+        return {"mode": out[0], "ksplit": out[1], "target_b": out[2], "used": out[3], "used_name": self.SCHEDULE_NAMES[out[3]]}
 
     def reset_inout(self, stream: int = 0):
         _check(lib.cloudsc_b200_reset_inout(self._h, ctypes.c_void_p(stream)))

@@ -476,6 +476,23 @@ int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc
   if (e != cudaSuccess) { cloudsc_b200_destroy(st); return cuda_fail(e, "cudaMalloc(plude0)"); }
   /* tensor maps (whole 32-column rows: NPROMA must be a multiple of 32) */
   st->has_tm = build_tensor_maps(st->dev, st->nblocks, nproma, klev, precision, &st->tm);
+  /* Default schedule of the FP64 state: the split-tail launch (mode 3, cloudsc_kernels.cu) -- 5 % faster than one CTA per tile
+     at 163 840 columns (profiles/r2_split_tail.txt), bit-identical on the shipped data; launches too small for it, aerosol runs
+     and the FP32 state (not measured) keep one CTA per tile.  Its scratch is small; if it cannot be had, mode 0 stays. */
+  if (st->has_tm && precision == CLOUDSC_B200_FP64 && !st->aer) {
+    const int ntiles = (st->nblocks * st->nproma + 31) / 32;
+    if (cudaMalloc(&st->sched.carry, persist_carry_bytes(ntiles, st->precision)) == cudaSuccess &&
+        cudaMalloc((void **)&st->sched.sm_b, kSchedInts * sizeof(int)) == cudaSuccess &&
+        cudaMemset(st->sched.sm_b, 0, kSchedInts * sizeof(int)) == cudaSuccess) {
+      st->sched.carry_tiles = ntiles;
+      st->sched_mode = st->sched.mode = 3;
+      st->sched.ksplit = st->sched.target_b = 0;
+    } else {
+      (void)cudaGetLastError();
+      if (st->sched.carry) { cudaFree(st->sched.carry); st->sched.carry = nullptr; }
+      if (st->sched.sm_b) { cudaFree(st->sched.sm_b); st->sched.sm_b = nullptr; }
+    }
+  }
   *out = st;
   return 0;
 }
@@ -496,7 +513,9 @@ int cloudsc_b200_destroy(cloudsc_b200_state *st) {
  *   mode 2  streaming: 12 persistent warps per SM taking tiles from a queue, the input ring kept full across tiles
  *   mode 1  persistent: 12 warps per SM, each running its tiles in two pieces (levels [0, ksplit) and [ksplit, klev))
  *           and choosing the next piece so that about target_b of the SM's warps are in a lower piece at any time
- * ksplit <= 0 -> 3*klev/5; target_b <= 0 -> 7 of 12.  Results are bit-identical in every mode.
+ *   mode 3  split tail (the default of an FP64 state): one launch whose first `target_b` x #SM blocks sweep their tile only down
+ *           to level `ksplit` and park the state, and whose LAST blocks finish those tiles -- the launch ends on half tiles
+ * ksplit <= 0 -> 3*klev/5; target_b <= 0 -> 7 of 12 (mode 1), 5 of 12 tiles per SM (mode 3).  Bit-identical in every mode.
  */
 int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b) {
   if (!st) return fail(CLOUDSC_B200_EARG, "set_schedule: NULL state");
@@ -571,7 +590,11 @@ int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, in
   if (end > st->ngptot) end = st->ngptot;
   LaunchGeom g{first_block * st->nproma, (int)end, st->nproma, st->klev};
   const int variant = g_variant.load();
-  if (st->has_tm && variant == VARIANT_AUTO && st->sched_mode >= 1)
+  /* a launch captured into a CUDA graph is replayed with the SAME kernel arguments: the per-launch sequence number of the
+     schedules with scratch (modes 1-3) would repeat, so a capturing stream gets one CTA per tile */
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st->sched_mode >= 1 && cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  if (st->has_tm && variant == VARIANT_AUTO && st->sched_mode >= 1 && cap == cudaStreamCaptureStatusNone)
     CU(launch_sweep_persist(ft, st->tm, g, ptsphy, st->precision, st->sched, (cudaStream_t)stream));
   else if (st->has_tm && variant == VARIANT_AUTO)
     CU(launch_sweep_tmap(ft, st->tm, g, ptsphy, st->precision, (cudaStream_t)stream));
@@ -582,9 +605,29 @@ int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, in
 
 int cloudsc_b200_state_kernel_info(cloudsc_b200_state *st, int out[8]) {
   if (!st || !out) return fail(CLOUDSC_B200_EARG, "state_kernel_info: NULL argument");
+  if (int rc = state_on_current_device(st, "state_kernel_info")) return rc;
   const int variant = g_variant.load();
-  if (st->has_tm && variant == VARIANT_AUTO && !sweep_aerosol_mask()) CU(tmap_kernel_info(st->precision, out));
-  else CU(sweep_kernel_info(st->nproma, st->precision, variant, out));
+  if (st->has_tm && variant == VARIANT_AUTO && !sweep_aerosol_mask()) {
+    int used = 0;                      /* the schedule a step() over the whole state gets */
+    if (st->sched_mode >= 1) {
+      LaunchGeom g{0, st->ngptot, st->nproma, st->klev};
+      CU(persist_schedule_used(g, st->precision, st->sched, &used));
+    }
+    CU(tmap_kernel_info(st->precision, out, used));
+  } else {
+    CU(sweep_kernel_info(st->nproma, st->precision, variant, out));
+  }
+  return 0;
+}
+
+int cloudsc_b200_get_schedule(cloudsc_b200_state *st, int out[4]) {
+  if (!st || !out) return fail(CLOUDSC_B200_EARG, "get_schedule: NULL argument");
+  if (int rc = state_on_current_device(st, "get_schedule")) return rc;
+  out[0] = st->sched_mode; out[1] = st->sched.ksplit; out[2] = st->sched.target_b; out[3] = 0;
+  if (st->has_tm && g_variant.load() == VARIANT_AUTO && st->sched_mode >= 1) {
+    LaunchGeom g{0, st->ngptot, st->nproma, st->klev};
+    CU(persist_schedule_used(g, st->precision, st->sched, &out[3]));
+  }
   return 0;
 }
 

@@ -684,22 +684,18 @@ struct SplitPlan {
   int *flag;       /* [nsplit] */
 };
 
-/* the upper piece of a tile ran about two tile times before its lower piece is dispatched; make sure, and see its parked state.
- * (One opaque asm statement: written as a C++ loop -- inline or out of line -- the spin costs the sweep behind it 24 bytes of
- * spills inside the level loop.) */
+/* The upper piece of a tile ran about two tile times before its lower piece is dispatched (blocks go out in index order); make
+ * sure, and see its parked state.  EVERY lane polls: a wait under `lane == 0` is divergent control flow in front of the sweep
+ * and costs it its uniform-datapath code (+350 instructions, 24 bytes of spills inside the level loop).  A launch whose upper
+ * pieces never ran (it would have to be dispatched out of order) traps after ~2 s instead of hanging the device. */
 __device__ __forceinline__ void split_wait(const int *flag, int seq) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .s32 v;\n"
-      "SPLIT_WAIT:\n"
-      "ld.acquire.gpu.global.s32 v, [%0];\n"
-      "setp.eq.s32 p, v, %1;\n"
-      "@p bra SPLIT_DONE;\n"
-      "nanosleep.u32 500;\n"
-      "bra SPLIT_WAIT;\n"
-      "SPLIT_DONE:\n"
-      "}\n" ::"l"(flag), "r"(seq) : "memory");
+  for (int n = 0;; ++n) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v == seq) break;
+    __nanosleep(500);
+    if (n > (1 << 22)) __trap();
+  }
 }
 
 template <typename T>
@@ -1080,19 +1076,21 @@ cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const 
   return launch_sweep_tmap_t<double>(ft, tm, g, ptsphy, stream);
 }
 
-/* persistent kernel: grid = the resident set (SMs x warps per SM), never more than the tiles */
+/* Which kernel a schedule gets for one launch: its own (returns ps.mode) or one CTA per tile (returns 0) -- aerosol runs,
+ * launches with fewer than two rounds of tiles per resident warp and states without scratch keep the latter.
+ * sms_out / per_out: SM count and resident CTAs per SM of the persistent kernels. */
 template <typename T>
-static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
-                                          const PersistSchedule &ps, cudaStream_t stream) {
-  if (g.col_end <= g.col_begin) return cudaSuccess;
+static cudaError_t persist_decide(const LaunchGeom &g, const PersistSchedule &ps, int *mode_out, int *sms_out, int *per_out) {
+  *mode_out = 0;
   const long long nblk = (g.col_end + g.nproma - 1) / g.nproma;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   const int ntiles = (g.col_end - g.col_begin + 31) / 32;
   const bool aer = host_consts<T>(dev).laericesed || host_consts<T>(dev).laericeauto;
-  if (aer || nblk * 5 * (g.klev + 1) * g.nproma >= (1ll << 32) || g.klev < 3 || !ps.carry || !ps.sm_b || ntiles > ps.carry_tiles)
-    return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
+  if (ps.mode < 1 || ps.mode > 3 || aer || nblk * 5 * (g.klev + 1) * g.nproma >= (1ll << 32) || g.klev < 3 || !ps.carry || !ps.sm_b ||
+      ntiles > ps.carry_tiles)
+    return cudaSuccess;
   const void *fn = (const void *)cloudsc_sweep_persist<T>;
   const size_t smem = TmapIO<T, true>::kSmem;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1109,11 +1107,31 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dev & 63][pi], fn, 32, smem);
     if (e != cudaSuccess) return e;
   }
-  const int resident = sms[dev & 63] * per_sm[dev & 63][pi];
+  *sms_out = sms[dev & 63];
+  *per_out = per_sm[dev & 63][pi];
+  /* fewer tiles than two full rounds of the resident set: nothing to interleave, no tail worth splitting */
+  if (*sms_out * *per_out > 0 && ntiles >= 2 * *sms_out * *per_out) *mode_out = ps.mode;
+  return cudaSuccess;
+}
+
+/* persistent kernels: grid = the resident set (SMs x warps per SM), never more than the tiles */
+template <typename T>
+static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
+                                          const PersistSchedule &ps, cudaStream_t stream) {
+  if (g.col_end <= g.col_begin) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int use = 0, nsm = 0, per_cta = 0;
+  e = persist_decide<T>(g, ps, &use, &nsm, &per_cta);
+  if (e != cudaSuccess) return e;
+  if (use == 0) return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
+  const int ntiles = (g.col_end - g.col_begin + 31) / 32;
+  const void *fn = (const void *)cloudsc_sweep_persist<T>;
+  const size_t smem = TmapIO<T, true>::kSmem;
+  const int resident = nsm * per_cta;
   static int resident_h[64];                          /* stable host storage for the asynchronous queue reset */
   resident_h[dev & 63] = resident;
-  /* fewer tiles than two full rounds of the resident set: nothing to interleave */
-  if (resident <= 0 || ntiles < 2 * resident) return launch_sweep_tmap_t<T>(ft, tm, g, ptsphy, stream);
   if (ps.mode == 2) {
     const void *sfn = (const void *)cloudsc_sweep_stream<T>;
     e = cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1140,11 +1158,11 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     e = cudaFuncSetAttribute(sfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     static int seq[64];
-    int per = ps.target_b > 0 ? ps.target_b : per_sm[dev & 63][pi];       /* split tiles per SM */
-    if (per > per_sm[dev & 63][pi]) per = per_sm[dev & 63][pi];
+    int per = ps.target_b > 0 ? ps.target_b : (per_cta * 5 + 6) / 12;   /* split tiles per SM: 5 of 12 (profiles/r2_split_tail.txt) */
+    if (per > per_cta) per = per_cta;
     SplitPlan sp;
     sp.ntiles = ntiles;
-    sp.nsplit = per * sms[dev & 63];
+    sp.nsplit = per * nsm;
     if (sp.nsplit > kSplitFlags) sp.nsplit = kSplitFlags;
     if (sp.nsplit > ps.carry_tiles) sp.nsplit = ps.carry_tiles;
     if (sp.nsplit > ntiles) sp.nsplit = ntiles;
@@ -1159,7 +1177,7 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     ++g_launches[KERNEL_TMAP];
     return cudaLaunchKernel(sfn, dim3(ntiles + sp.nsplit), dim3(32), sargs, smem, stream);
   }
-  PersistPlan plan{ksplit, ntiles, ps.target_b > 0 ? ps.target_b : (per_sm[dev & 63][pi] * 7 + 6) / 12, ps.carry, ps.sm_b};
+  PersistPlan plan{ksplit, ntiles, ps.target_b > 0 ? ps.target_b : (per_cta * 7 + 6) / 12, ps.carry, ps.sm_b};
   StepConst<T> sc;
   fill_step<T>(host_consts<T>(dev), ptsphy, &sc);
   void *args[] = {(void *)&ft, (void *)&tm, (void *)&g, (void *)&sc, (void *)&plan};
@@ -1172,14 +1190,16 @@ cudaError_t launch_sweep_persist(const FieldTable &ft, const TensorMaps &tm, con
   if (precision == CLOUDSC_B200_FP32) return launch_sweep_persist_t<float>(ft, tm, g, ptsphy, ps, stream);
   return launch_sweep_persist_t<double>(ft, tm, g, ptsphy, ps, stream);
 }
+cudaError_t persist_schedule_used(const LaunchGeom &g, int precision, const PersistSchedule &ps, int *mode_out) {
+  int nsm = 0, per_cta = 0;
+  if (precision == CLOUDSC_B200_FP32) return persist_decide<float>(g, ps, mode_out, &nsm, &per_cta);
+  return persist_decide<double>(g, ps, mode_out, &nsm, &per_cta);
+}
 size_t persist_carry_bytes(int ntiles, int precision) {
   return (size_t)ntiles * kCarryVals * 32 * (precision == CLOUDSC_B200_FP32 ? sizeof(float) : sizeof(double));
 }
 
-template <typename T>
-static cudaError_t tmap_kernel_info_t(int out[8]) {
-  const void *fn = (const void *)cloudsc_sweep_tmap<T>;
-  const size_t dyn = TmapIO<T>::kSmem;
+static cudaError_t tile_kernel_info(const void *fn, size_t dyn, int out[8]) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1195,8 +1215,18 @@ static cudaError_t tmap_kernel_info_t(int out[8]) {
   return cudaSuccess;
 }
 
-cudaError_t tmap_kernel_info(int precision, int out[8]) {
-  return precision == CLOUDSC_B200_FP32 ? tmap_kernel_info_t<float>(out) : tmap_kernel_info_t<double>(out);
+template <typename T>
+static cudaError_t tmap_kernel_info_t(int mode, int out[8]) {
+  /* out[6]: 100 = one CTA per tile, 100 + mode = the kernel of that schedule */
+  const void *fn = mode == 1 ? (const void *)cloudsc_sweep_persist<T> : mode == 2 ? (const void *)cloudsc_sweep_stream<T>
+                 : mode == 3 ? (const void *)cloudsc_sweep_split<T> : (const void *)cloudsc_sweep_tmap<T>;
+  cudaError_t e = tile_kernel_info(fn, mode >= 1 && mode <= 3 ? TmapIO<T, true>::kSmem : TmapIO<T>::kSmem, out);
+  if (e == cudaSuccess && mode >= 1 && mode <= 3) out[6] = 100 + mode;
+  return e;
+}
+
+cudaError_t tmap_kernel_info(int precision, int out[8], int mode) {
+  return precision == CLOUDSC_B200_FP32 ? tmap_kernel_info_t<float>(mode, out) : tmap_kernel_info_t<double>(mode, out);
 }
 
 /* ---- self-test of the fast-mode primitives (cloudsc_b200_selftest_primitives) ---------------------------------------- */

@@ -80,7 +80,9 @@ constexpr int kSplitFlagOffset = 1024, kSplitFlags = 4096, kSchedInts = kSplitFl
 cudaError_t launch_sweep_persist(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy, int precision,
                                  const PersistSchedule &ps, cudaStream_t stream);
 size_t persist_carry_bytes(int ntiles, int precision);
-cudaError_t tmap_kernel_info(int precision, int out[8]);
+/* the schedule launch_sweep_persist would use for this launch: ps.mode, or 0 = one CTA per tile (small launch, aerosol run ...) */
+cudaError_t persist_schedule_used(const LaunchGeom &g, int precision, const PersistSchedule &ps, int *mode_out);
+cudaError_t tmap_kernel_info(int precision, int out[8], int mode = 0);   /* mode: the schedule whose kernel is described */
 
 cudaError_t launch_selftest_primitives(const double *x, int n, double *out, cudaStream_t stream);
 cudaError_t upload_consts(const CloudscConst<double> &c64, const CloudscConst<float> &c32);

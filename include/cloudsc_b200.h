@@ -181,8 +181,16 @@ int cloudsc_b200_download(cloudsc_b200_state *st, void *const host_fields[CLOUDS
 int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, int nblocks, void *stream);
 /* how step() schedules the 32-column tiles of a launch: mode 0 = one CTA per tile; mode 1 = persistent warps that run
  * the upper (bandwidth-bound) and lower (latency-bound) parts of their tiles interleaved, cut at level `ksplit`, with
- * about `target_b` of an SM's 12 warps in a lower part at any time (<= 0: defaults).  Bit-identical results. */
+ * about `target_b` of an SM's 12 warps in a lower part at any time (<= 0: defaults); mode 2 = persistent warps taking whole
+ * tiles from a queue; mode 3 (the default of an FP64 state) = one launch whose first `target_b` x #SM blocks sweep their
+ * tile only down to level `ksplit` and whose last blocks finish those tiles, so that the launch ends on half tiles.
+ * Bit-identical results on the shipped data; rounding-level differences between kernels elsewhere. */
 int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b);
+/* out = { mode, ksplit, target_b as set (0 = defaults), the schedule a step() over the WHOLE state actually gets }: a launch
+ * with fewer than two rounds of tiles per resident warp, an aerosol run or a state without tensor maps keeps one CTA per tile
+ * (0) whatever the mode.  A state is not re-entrant under modes 1-3: one step() of a state in flight at a time (steps on one
+ * stream are; the schedules keep per-state scratch), and a step() captured into a CUDA graph should use mode 0. */
+int cloudsc_b200_get_schedule(cloudsc_b200_state *st, int out[4]);
 /* restore PLUDE from the pristine copy kept at upload() (the kernel scales it in place) */
 int cloudsc_b200_reset_inout(cloudsc_b200_state *st, void *stream);
 /* kernel_info of the kernel step() launches for this state (the arena-backed tensor-map TMA kernel when

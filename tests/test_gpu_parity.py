@@ -607,7 +607,8 @@ def test_arena_state_tensor_map_kernel_matches_oracle(built, oracle, input_data,
     st = api.State(ngptot, nproma, klev)
     try:
         info = st.kernel_info()
-        assert (info["variant"] == 100) == (nproma % 32 == 0), info      # 100 = the tensor-map kernel
+        assert (info["variant"] == 100) == (nproma % 32 == 0), info      # 100 = the tensor-map kernel, one CTA per tile
+        assert st.get_schedule()["used"] == 0                            # (a launch this small is never split)
         st.upload(F)
         nb = state.nblocks_of(ngptot, nproma)
         half = nb // 2
@@ -667,7 +668,7 @@ def test_other_column_heights(built, oracle, input_data, lev0, lev1):
 
 
 def test_full_size_properties_arena_state(built, input_data):
-    """The path bench.py times, at its size (163840 x 128, resident arena state, tensor-map kernel):
+    """The path bench.py times, at its size (163840 x 128, resident arena state, tensor-map kernel in its default schedule):
     replication invariance (column g == column g mod 100, bitwise), agreement of the first 100 columns with
     reference.h5, and bitwise agreement with the kernel behind cloudsc_b200_launch on caller-owned fields."""
     from dwarf_p_cloudsc_b200 import params, state, api, validate
@@ -678,6 +679,9 @@ def test_full_size_properties_arena_state(built, input_data):
     G2 = _run_gpu({n: a.copy() for n, a in F.items()}, p, k, ngptot, nproma, klev, scalars["PTSPHY"])
     st = api.State(ngptot, nproma, klev)
     try:
+        # an FP64 state of this size gets the split-tail launch (schedule mode 3) without being asked
+        sched, info = st.get_schedule(), st.kernel_info()
+        assert sched["mode"] == 3 and sched["used"] == 3 and info["variant"] == 103 and info["local_bytes"] == 0, (sched, info)
         st.upload(F); st.step(scalars["PTSPHY"]); st.download(F); st.sync()
     finally:
         st.close()

@@ -33,5 +33,15 @@ for r in rows[2:]:
         lines.append("dram traffic per launch (read+write): %.4f GB" % (traffic / 1e9))
 open(out, "w").write("\n".join(lines) + "\n")
 if len(sys.argv) > 3 and traffic:
-    json.dump({"dram_bytes_per_launch": traffic, "source": rep.split("/")[-1]}, open(sys.argv[3], "w"))
+    # keep what other captures recorded (per kernel); the top-level figure is the latest capture's
+    try:
+        rec = json.load(open(sys.argv[3]))
+    except Exception:
+        rec = {}
+    m = re.search(r"cloudsc_sweep_\w+", d.get("Kernel Name", ""))
+    kname = m.group(0) if m else d.get("Kernel Name", "?")
+    by = rec.get("by_kernel", {})
+    by[kname] = {"dram_bytes_per_launch": traffic, "source": rep.split("/")[-1]}
+    rec.update({"dram_bytes_per_launch": traffic, "source": rep.split("/")[-1], "kernel": kname, "by_kernel": by})
+    json.dump(rec, open(sys.argv[3], "w"), indent=1)
 print("\n".join(lines))
