@@ -1077,7 +1077,7 @@ cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const 
 }
 
 /* Which kernel a schedule gets for one launch: its own (returns ps.mode) or one CTA per tile (returns 0) -- aerosol runs,
- * launches with fewer than two rounds of tiles per resident warp and states without scratch keep the latter.
+ * launches too small for the schedule (below) and states without scratch keep the latter.
  * sms_out / per_out: SM count and resident CTAs per SM of the persistent kernels. */
 template <typename T>
 static cudaError_t persist_decide(const LaunchGeom &g, const PersistSchedule &ps, int *mode_out, int *sms_out, int *per_out) {
@@ -1109,8 +1109,18 @@ static cudaError_t persist_decide(const LaunchGeom &g, const PersistSchedule &ps
   }
   *sms_out = sms[dev & 63];
   *per_out = per_sm[dev & 63][pi];
-  /* fewer tiles than two full rounds of the resident set: nothing to interleave, no tail worth splitting */
-  if (*sms_out * *per_out > 0 && ntiles >= 2 * *sms_out * *per_out) *mode_out = ps.mode;
+  /* The persistent kernels (modes 1, 2) need two full rounds of the resident set to have anything to interleave.  The
+     split-tail launch pays as soon as there is a second round at all -- 1 792 tiles (1.01 rounds) x1.19, 2 048 x1.15,
+     2 816 x1.06, 3 752 x1.15, 5 120 x1.05, 20 480 x1.02 -- and costs 2-3 % when every tile is resident at once (1 024 tiles:
+     profiles/r2_split_small.txt).  Measurement knob: CLOUDSC_B200_SPLIT_MIN_TILES=<n> moves its bar. */
+  const int resident = *sms_out * *per_out;
+  int min_tiles = 2 * resident;
+  if (ps.mode == 3) {
+    min_tiles = resident + 1;
+    static const int env_min = [] { const char *v = getenv("CLOUDSC_B200_SPLIT_MIN_TILES"); return v ? atoi(v) : 0; }();
+    if (env_min > 0) min_tiles = env_min;
+  }
+  if (resident > 0 && ntiles >= min_tiles) *mode_out = ps.mode;
   return cudaSuccess;
 }
 

@@ -65,7 +65,8 @@ extern const int kArenaGroupC[2];
 cudaError_t launch_sweep_tmap(const FieldTable &ft, const TensorMaps &tm, const LaunchGeom &g, double ptsphy,
                               int precision, cudaStream_t stream);
 /* persistent variant of the tensor-map kernel (cloudsc_kernels.cu, "persistent kernel"); falls back to launch_sweep_tmap
- * for launches with fewer than two rounds of tiles per resident warp.  ksplit / target_b <= 0: defaults. */
+ * for launches too small for the schedule (modes 1, 2: fewer than two rounds of tiles per resident warp; mode 3: every tile
+ * resident at once).  ksplit / target_b <= 0: defaults. */
 struct PersistSchedule {
   int mode;         /* 1: interleaved upper / lower pieces (cloudsc_sweep_persist); 2: streaming tile queue (cloudsc_sweep_stream);
                        3: split tail (cloudsc_sweep_split; ksplit = cut level, target_b = split tiles per SM) */

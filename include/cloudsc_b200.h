@@ -187,7 +187,8 @@ int cloudsc_b200_step(cloudsc_b200_state *st, double ptsphy, int first_block, in
  * Bit-identical results on the shipped data; rounding-level differences between kernels elsewhere. */
 int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int target_b);
 /* out = { mode, ksplit, target_b as set (0 = defaults), the schedule a step() over the WHOLE state actually gets }: a launch
- * with fewer than two rounds of tiles per resident warp, an aerosol run or a state without tensor maps keeps one CTA per tile
+ * too small for the schedule (modes 1, 2: fewer than two rounds of tiles per resident warp; mode 3: every tile resident at
+ * once, i.e. <= 56 832 columns on 148 SMs in FP64), an aerosol run or a state without tensor maps keeps one CTA per tile
  * (0) whatever the mode.  A state is not re-entrant under modes 1-3: one step() of a state in flight at a time (steps on one
  * stream are; the schedules keep per-state scratch), and a step() captured into a CUDA graph should use mode 0. */
 int cloudsc_b200_get_schedule(cloudsc_b200_state *st, int out[4]);

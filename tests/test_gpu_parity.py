@@ -756,12 +756,14 @@ def test_level0_link_of_the_reference_driver(built, args):
 
 
 @pytest.mark.parametrize("ngptot,nproma,perturbation,ksplit,target_b", [(163840, 128, "", 0, 0), (120000, 64, "warm+land+conv+rain+moist+tend", 40, 3),
-                                                                        (131071, 32, "sparse+warm+conv", 136, 12), (114688, 128, "hot+rain+moist+conv", 1, 1)])
+                                                                        (131071, 32, "sparse+warm+conv", 136, 12), (114688, 128, "hot+rain+moist+conv", 1, 1),
+                                                                        (60000, 32, "warm+land+conv+rain+moist+tend", 70, 4)])
 def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma, perturbation, ksplit, target_b):
     """cloudsc_b200_set_schedule(mode 1 / mode 2 / mode 3): persistent warps that take their tiles from a queue with the input
     ring kept full across tiles (2), one launch whose last blocks are the lower halves of tiles split at a cut (3), or warps
     that run the upper and lower parts of their column tiles interleaved, the state at the cut going through a device buffer (launches big enough for the persistent path:
-    >= 2 tiles per resident warp; incl. a ragged last tile).  Any cut level and any mix target gives the SAME bits
+    >= 2 tiles per resident warp; incl. a ragged last tile; the 60 000-column case has 1.06 rounds of tiles, where only the split
+    tail applies and modes 1 / 2 fall back to one CTA per tile).  Any cut level and any mix target gives the SAME bits
     (the schedule never enters the arithmetic; the CPU proof that a cut sweep equals the uncut one is
     test_cut_sweep_is_bit_identical) and, on the shipped data, the bits of the one-CTA-per-tile kernel and of the streaming
     kernel.  On synthetic inputs that reach the warm-phase code different kernels differ by rounding (4e-16: the compiler
@@ -776,6 +778,7 @@ def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma,
     outs = [f.name for f in params.OUTPUT_FIELDS]
     try:
         st.upload(F)
+        assert st.get_schedule()["used"] == 3      # the default of an FP64 state with more tiles than resident warps
         res = []
         for mode, ks, tb in ((0, 0, 0), (1, ksplit, target_b), (1, max(1, klev - 1 - ksplit), 12 - min(target_b, 11)), (2, 0, 0),
                              (3, ksplit, 0), (3, max(1, klev - 1 - ksplit), 5)):

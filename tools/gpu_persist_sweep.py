@@ -44,6 +44,8 @@ if "--split" in sys.argv:
     settings = [(3, 82, 4), (3, 82, 3), (3, 82, 2), (3, 82, 5), (3, 95, 4), (3, 105, 4), (3, 70, 4), (3, 60, 4), (3, 95, 3), (3, 105, 6), (3, 82, 4)]
 if "--confirm" in sys.argv:      # the default of an FP64 state (3, 0, 0) beside its neighbours and one CTA per tile, alternated
     settings = [(3, 0, 0), (0, 0, 0), (3, 82, 5), (3, 82, 6), (3, 82, 4), (0, 0, 0), (3, 0, 0)]
+if "--small" in sys.argv:        # launches below two rounds of tiles (run with CLOUDSC_B200_SPLIT_MIN_TILES=1): where does splitting stop paying
+    settings = [(3, 0, 0), (3, 82, 3), (3, 82, 8), (3, 82, 12), (3, 60, 5), (3, 100, 5), (0, 0, 0), (3, 0, 0)]
 if "--full" in sys.argv:
     settings = [(1, 0, 0)] + [(1, ks, tb) for ks in (82, 70, 90, 60) for tb in (4, 6, 7, 8, 12, 1)]
 for mode, ks, tb in settings:
