@@ -10,6 +10,7 @@
 #include "cloudsc_kernels.cuh"
 #include "cloudsc_column.cuh"
 #include "cloudsc_fill.h"
+#include "cloudsc_split_plan.h"
 
 #include <atomic>
 #include <cstdint>
@@ -704,11 +705,8 @@ cloudsc_sweep_split(const __grid_constant__ FieldTable ft, const __grid_constant
                     const __grid_constant__ StepConst<T> sc, const __grid_constant__ SplitPlan plan) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using IO = TmapIO<T, true>;
-  const int b = (int)blockIdx.x;
-  const bool tail = b >= plan.ntiles;
-  const int tile = tail ? b - plan.ntiles : b;
-  const bool split = tile < plan.nsplit;
-  const int kb = tail ? plan.cut : 0, ke = (split && !tail) ? plan.cut : g.klev;
+  /* the block plan (cloudsc_split_plan.h; declares b, tail, tile, split, kb, ke -- the text split_piece() expands for the host) */
+  CLOUDSC_SPLIT_PIECE((int)blockIdx.x, plan.ntiles, plan.nsplit, plan.cut, g.klev);
   const int ccol = g.col_begin + tile * IO::kCols;
   if (ccol >= g.col_end) return;
   const int ibl = ccol / g.nproma;
@@ -1158,9 +1156,7 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     ++g_launches[KERNEL_TMAP];
     return cudaLaunchKernel(sfn, dim3(resident), dim3(32), sargs, smem, stream);
   }
-  int ksplit = ps.ksplit > 0 ? ps.ksplit : (3 * g.klev) / 5;
-  if (ksplit < 1) ksplit = 1;
-  if (ksplit > g.klev - 1) ksplit = g.klev - 1;
+  const int ksplit = split_cut(ps.ksplit, g.klev);
   if (ps.mode == 3) {
     const void *sfn = (const void *)cloudsc_sweep_split<T>;
     e = cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1168,14 +1164,9 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     e = cudaFuncSetAttribute(sfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     static int seq[64];
-    int per = ps.target_b > 0 ? ps.target_b : (per_cta * 5 + 6) / 12;   /* split tiles per SM: 5 of 12 (profiles/r2_split_tail.txt) */
-    if (per > per_cta) per = per_cta;
     SplitPlan sp;
     sp.ntiles = ntiles;
-    sp.nsplit = per * nsm;
-    if (sp.nsplit > kSplitFlags) sp.nsplit = kSplitFlags;
-    if (sp.nsplit > ps.carry_tiles) sp.nsplit = ps.carry_tiles;
-    if (sp.nsplit > ntiles) sp.nsplit = ntiles;
+    sp.nsplit = split_count(ntiles, nsm, per_cta, ps.target_b, kSplitFlags, ps.carry_tiles);   /* 5 of 12 tiles per SM (profiles/r2_split_tail.txt) */
     sp.cut = ksplit;
     sp.seq = ++seq[dev & 63];
     if (sp.seq == 0) sp.seq = ++seq[dev & 63];
@@ -1185,7 +1176,7 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     fill_step<T>(host_consts<T>(dev), ptsphy, &sc3);
     void *sargs[] = {(void *)&ft, (void *)&tm, (void *)&g, (void *)&sc3, (void *)&sp};
     ++g_launches[KERNEL_TMAP];
-    return cudaLaunchKernel(sfn, dim3(ntiles + sp.nsplit), dim3(32), sargs, smem, stream);
+    return cudaLaunchKernel(sfn, dim3(split_blocks(ntiles, sp.nsplit)), dim3(32), sargs, smem, stream);
   }
   PersistPlan plan{ksplit, ntiles, ps.target_b > 0 ? ps.target_b : (per_cta * 7 + 6) / 12, ps.carry, ps.sm_b};
   StepConst<T> sc;

@@ -12,7 +12,9 @@
 #include <cstring>
 #include "cloudsc_b200.h"
 #include "cloudsc_column.cuh"
+#include <vector>
 #include "cloudsc_fill.h"
+#include "cloudsc_split_plan.h"
 
 namespace {
 using namespace cloudsc;
@@ -127,6 +129,68 @@ int run_ranged(const struct TECLDP *p, const struct cloudsc_consts *k, void *con
   return 0;
 }
 
+/* The split-tail launch (schedule mode 3) on a pretend machine of `nsm` SMs with `per_sm` resident one-warp CTAs: the blocks of
+ * the launch are walked in index order through split_piece() / split_count() / split_cut() -- the plan the device runs
+ * (cloudsc_split_plan.h) -- each block sweeping the 32 columns of its tile over its level range.  The parked state of a split
+ * tile lives in `carry[tile]`, its flag is set by the upper piece and REQUIRED by the lower one (a plan that ran a lower
+ * piece first would return -2 here and spin on the device); scratch is poisoned at every block start, and so is a carry
+ * once it was consumed.  info[4] = { blocks, nsplit, cut, pieces that loaded a carry }. */
+template <typename T>
+int run_split(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
+              int ngptot, int nproma, int klev, double ptsphy, int nsm, int per_sm, int ksplit, int target_b, int info[4]) {
+  if (check_params(p) || aerosol_mask(p)) return CLOUDSC_B200_EPARAMS;
+  if (nsm < 1 || per_sm < 1 || klev < 3) return CLOUDSC_B200_EARG;
+  CloudscConst<T> c;
+  fill_consts<T>(p, k, &c);
+  StepConst<T> sc;
+  fill_step<T>(c, ptsphy, &sc);
+  const int ntiles = (ngptot + 31) / 32;
+  const int nsplit = split_count(ntiles, nsm, per_sm, target_b, 4096, ntiles);
+  const int cut = split_cut(ksplit, klev);
+  const int nblocks = split_blocks(ntiles, nsplit);
+  constexpr int kVals = 8 + PARK_COUNT;
+  std::vector<T> carry((size_t)nsplit * 32 * kVals, T(-7.0e300));
+  std::vector<int> flag(nsplit, 0);
+  std::vector<int> covered((size_t)ntiles * klev, 0);
+  int loads = 0;
+  for (int b = 0; b < nblocks; b++) {
+    const SplitPiece pc = split_piece(b, ntiles, nsplit, cut, klev);
+    if (pc.tile < 0 || pc.tile >= ntiles || pc.kb < 0 || pc.ke > klev || pc.kb >= pc.ke) return -3;
+    if (pc.lower) {
+      if (pc.tile >= nsplit || flag[pc.tile] != 1) return -2;   /* the upper piece has not run */
+      flag[pc.tile] = 2;
+      ++loads;
+    }
+    for (int kk = pc.kb; kk < pc.ke; kk++) ++covered[(size_t)pc.tile * klev + kk];
+    for (int lane = 0; lane < 32; lane++) {
+      const int col = pc.tile * 32 + lane;
+      if (col >= ngptot) break;
+      const int blk = col / nproma, jl = col - blk * nproma;
+      void *pb[CLOUDSC_NFIELDS];
+      for (int f = 0; f < CLOUDSC_NFIELDS; f++) {
+        const size_t off = (size_t)blk * cloudsc_b200_field_block_elems(f, nproma, klev);
+        const size_t es = cloudsc_b200_field_kind(f) == 'I' ? sizeof(int) : sizeof(T);
+        pb[f] = fields[f] ? (void *)((char *)fields[f] + off * es) : nullptr;
+      }
+      HostIORanged<T> io;
+      io.f = pb; io.jl = jl; io.stride = nproma; io.klev = klev;
+      io.kb = pc.kb; io.ke = pc.ke;
+      io.buf = (pc.upper || pc.lower) ? &carry[((size_t)pc.tile * 32 + lane) * kVals] : nullptr;
+      for (int i = 0; i < PARK_COUNT; i++) io.slots[i] = T(-1.0e300);
+      cloudsc_column<T>(c, sc, io, klev);
+      if (pc.lower) for (int i = 0; i < kVals; i++) io.buf[i] = T(-7.0e300);
+    }
+    if (pc.upper) {
+      if (flag[pc.tile] != 0) return -4;
+      flag[pc.tile] = 1;
+    }
+  }
+  for (int t = 0; t < nsplit; t++) if (flag[t] != 2) return -5;                  /* every parked state was consumed */
+  for (size_t i = 0; i < covered.size(); i++) if (covered[i] != 1) return -6;   /* every level of every tile exactly once */
+  if (info) { info[0] = nblocks; info[1] = nsplit; info[2] = cut; info[3] = loads; }
+  return 0;
+}
+
 template <typename T, bool PARKED = false>
 int run(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
         int ngptot, int nproma, int klev, double ptsphy) {
@@ -192,6 +256,20 @@ int cloudsc_emul_blocks_ranged_f64(const struct TECLDP *p, const struct cloudsc_
                                    int ngptot, int nproma, int klev, double ptsphy, int cut1, int cut2) {
   return run_ranged<double>(p, k, fields, ngptot, nproma, klev, ptsphy, cut1, cut2);
 }
+int cloudsc_emul_split_tail_f64(const struct TECLDP *p, const struct cloudsc_consts *k, void *const fields[CLOUDSC_NFIELDS],
+                                int ngptot, int nproma, int klev, double ptsphy, int nsm, int per_sm, int ksplit, int target_b,
+                                int info[4]) {
+  return run_split<double>(p, k, fields, ngptot, nproma, klev, ptsphy, nsm, per_sm, ksplit, target_b, info);
+}
+/* the plan alone: out[5] = { tile, kb, ke, lower, upper } of block b */
+void cloudsc_emul_split_piece(int b, int ntiles, int nsplit, int cut, int klev, int out[5]) {
+  const SplitPiece pc = split_piece(b, ntiles, nsplit, cut, klev);
+  out[0] = pc.tile; out[1] = pc.kb; out[2] = pc.ke; out[3] = pc.lower; out[4] = pc.upper;
+}
+int cloudsc_emul_split_count(int ntiles, int nsm, int per_sm, int target_b, int max_flags, int carry_tiles) {
+  return split_count(ntiles, nsm, per_sm, target_b, max_flags, carry_tiles);
+}
+int cloudsc_emul_split_cut(int ksplit, int klev) { return split_cut(ksplit, klev); }
 /* ---- per-process entry points (tests/test_unit_processes.py): the device code's sink limiter, implicit solve and
  * Newton step, called on their own.  a[13] = a01 a02 a03 a04 a12 a14 a23 a24 a34 d0 d1 d2 d3 (cloudsc_column.cuh). */
 void cloudsc_emul_unit_limiter(double a[13], const double qx5[5], double cs[5]) {

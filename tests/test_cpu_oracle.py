@@ -343,6 +343,76 @@ def test_cut_sweep_is_bit_identical(built, oracle, input_data, variant, cuts):
                 assert np.array_equal(state.unblock(oracle_out[f.name], ngptot), b), f.name
 
 
+@pytest.mark.parametrize("ntiles,nsm,per_sm,target_b,ksplit,klev", [(5120, 148, 12, 0, 0, 137), (1792, 148, 12, 0, 0, 137), (1777, 148, 12, 5, 82, 137),
+                                                                    (20480, 148, 12, 0, 0, 137), (20480, 148, 12, 12, 136, 137), (7, 2, 3, 0, 0, 137),
+                                                                    (5, 2, 3, 3, 1, 3), (1, 1, 1, 0, 0, 60), (100000, 148, 16, 16, 0, 91)])
+def test_split_tail_plan_covers_every_level_once(built, ntiles, nsm, per_sm, target_b, ksplit, klev):
+    """The block plan of the split-tail launch (csrc/cloudsc_split_plan.h: the text the kernel expands, reached here through the
+    host emulation library): every (tile, level) belongs to exactly one block; upper pieces are the FIRST blocks and lower
+    pieces the LAST ones (so that in dispatch order every upper piece has started before any lower piece is looked at, and the
+    launch ends on short pieces); the number of split tiles respects the flags, the scratch and the launch."""
+    import pyemul
+    em = pyemul.Emul()
+    cut = em.split_cut(ksplit, klev)
+    assert 1 <= cut <= klev - 1 and (ksplit <= 0 or cut == min(max(ksplit, 1), klev - 1)) and (ksplit > 0 or cut == max(1, min(3 * klev // 5, klev - 1)))
+    nsplit = em.split_count(ntiles, nsm, per_sm, target_b)
+    per = min(target_b if target_b > 0 else (per_sm * 5 + 6) // 12, per_sm)
+    assert nsplit == min(per * nsm, 4096, ntiles)
+    assert em.split_count(ntiles, nsm, per_sm, target_b, 64, 1 << 30) <= 64 and em.split_count(ntiles, nsm, per_sm, target_b, 4096, 3) <= 3
+    nblocks = ntiles + nsplit
+    cover = np.zeros((ntiles, klev), dtype=np.int32)
+    upper_at, lower_at = {}, {}
+    for b in range(nblocks):
+        pc = em.split_piece(b, ntiles, nsplit, cut, klev)
+        assert 0 <= pc["tile"] < ntiles and 0 <= pc["kb"] < pc["ke"] <= klev, (b, pc)
+        cover[pc["tile"], pc["kb"]:pc["ke"]] += 1
+        if pc["upper"]:
+            assert not pc["lower"] and (pc["kb"], pc["ke"]) == (0, cut) and b == pc["tile"] < nsplit
+            upper_at[pc["tile"]] = b
+        elif pc["lower"]:
+            assert (pc["kb"], pc["ke"]) == (cut, klev) and b >= ntiles and pc["tile"] == b - ntiles
+            lower_at[pc["tile"]] = b
+        else:
+            assert (pc["kb"], pc["ke"]) == (0, klev) and nsplit <= b < ntiles
+    assert (cover == 1).all()
+    assert sorted(upper_at) == sorted(lower_at) == list(range(nsplit))
+    if nsplit:
+        assert max(upper_at.values()) < nsplit <= ntiles <= min(lower_at.values())
+
+
+@pytest.mark.parametrize("machine", [(2, 3, 0, 0), (1, 2, 2, 136), (3, 2, 1, 1), (2, 12, 0, 40)])
+@pytest.mark.parametrize("variant,ngptot,nproma", [("", 300, 32), ("warm+land+conv+rain+moist+tend", 333, 64), ("sparse+warm+conv", 100, 100)])
+def test_split_tail_launch_is_bit_identical(built, oracle, input_data, variant, ngptot, nproma, machine):
+    """Schedule mode 3 end to end on the host: the blocks of a split-tail launch walked in dispatch order on a pretend machine
+    (nsm x per_sm resident CTAs, so that a few hundred columns make several rounds of tiles), every block sweeping its
+    32-column tile over its level range with the device column code, parked state through per-tile buffers guarded by the
+    flags.  Strict mode: bit-identical to the reference; fast mode: bit-identical to its own uncut sweep.  (Ragged last
+    tiles, tiles straddling NPROMA blocks, every tile split, one tile split.)"""
+    import pyemul
+    from dwarf_p_cloudsc_b200 import params, state
+    cols, scalars, klon, klev = input_data
+    p, k = params.params_from_scalars(scalars)
+    c2 = state.perturb(cols, variant) if variant else cols
+    A = state.blocked_fields(c2, ngptot, nproma, klev)
+    nsm, per_sm, target_b, ksplit = machine
+    ntiles = (ngptot + 31) // 32
+    oracle_out = {n: a.copy() for n, a in A.items()}
+    oracle.run(oracle_out, p, k, ngptot, nproma, klev, scalars["PTSPHY"], 1)
+    for fast in (False, True):
+        em = pyemul.Emul(fast=fast)
+        whole = {n: a.copy() for n, a in A.items()}
+        em.run(whole, p, k, ngptot, nproma, klev, scalars["PTSPHY"], parked=True)
+        split = {n: a.copy() for n, a in A.items()}
+        info = em.run_split_tail(split, p, k, ngptot, nproma, klev, scalars["PTSPHY"], nsm, per_sm, ksplit, target_b)
+        assert info["nsplit"] == em.split_count(ntiles, nsm, per_sm, target_b) > 0 and info["blocks"] == ntiles + info["nsplit"]
+        assert info["carry_loads"] == info["nsplit"] and info["cut"] == em.split_cut(ksplit, klev)
+        for f in params.OUTPUT_FIELDS:
+            a, b = state.unblock(whole[f.name], ngptot), state.unblock(split[f.name], ngptot)
+            assert np.array_equal(a, b), (fast, f.name, float(np.abs(a - b).max()))
+            if not fast:
+                assert np.array_equal(state.unblock(oracle_out[f.name], ngptot), b), f.name
+
+
 def test_fp32_reference_pins_the_single_precision_column_code(built, input_data):
     """oracle/_ref32 = the UNMODIFIED reference kernel re-typed to single precision by the preprocessor (what JPRB=real32
     does to the Fortran kernel).  (1) The strict host build of the device column code instantiated for float is that
