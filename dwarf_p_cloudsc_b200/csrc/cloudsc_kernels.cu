@@ -1163,13 +1163,13 @@ static cudaError_t launch_sweep_persist_t(const FieldTable &ft, const TensorMaps
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(sfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    static int seq[64];
+    static std::atomic<int> seq{0};   /* one value per launch, process-wide: two host threads never hand out the same one */
     SplitPlan sp;
     sp.ntiles = ntiles;
     sp.nsplit = split_count(ntiles, nsm, per_cta, ps.target_b, kSplitFlags, ps.carry_tiles);   /* 5 of 12 tiles per SM (profiles/r2_split_tail.txt) */
     sp.cut = ksplit;
-    sp.seq = ++seq[dev & 63];
-    if (sp.seq == 0) sp.seq = ++seq[dev & 63];
+    sp.seq = ++seq;
+    if (sp.seq == 0) sp.seq = ++seq;    /* 0 is what a fresh flag holds */
     sp.carry = ps.carry;
     sp.flag = ps.sm_b + kSplitFlagOffset;
     StepConst<T> sc3;
