@@ -483,7 +483,8 @@ int cloudsc_b200_create(int ngptot, int nproma, int klev, int precision, cloudsc
     const int ntiles = (st->nblocks * st->nproma + 31) / 32;
     if (cudaMalloc(&st->sched.carry, persist_carry_bytes(ntiles, st->precision)) == cudaSuccess &&
         cudaMalloc((void **)&st->sched.sm_b, kSchedInts * sizeof(int)) == cudaSuccess &&
-        cudaMemset(st->sched.sm_b, 0, kSchedInts * sizeof(int)) == cudaSuccess) {
+        cudaMemset(st->sched.sm_b, 0, kSchedInts * sizeof(int)) == cudaSuccess &&
+        cudaStreamSynchronize(cudaStreamLegacy) == cudaSuccess) {   /* (a step() on a non-blocking stream must find the flags zeroed) */
       st->sched.carry_tiles = ntiles;
       st->sched_mode = st->sched.mode = 3;
       st->sched.ksplit = st->sched.target_b = 0;
@@ -527,6 +528,7 @@ int cloudsc_b200_set_schedule(cloudsc_b200_state *st, int mode, int ksplit, int 
     CU(cudaMalloc(&st->sched.carry, persist_carry_bytes(ntiles, st->precision)));
     CU(cudaMalloc((void **)&st->sched.sm_b, kSchedInts * sizeof(int)));
     CU(cudaMemset(st->sched.sm_b, 0, kSchedInts * sizeof(int)));
+    CU(cudaStreamSynchronize(cudaStreamLegacy));
     st->sched.carry_tiles = ntiles;
   }
   st->sched_mode = mode;
