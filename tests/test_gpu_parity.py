@@ -756,8 +756,7 @@ def test_level0_link_of_the_reference_driver(built, args):
 
 
 @pytest.mark.parametrize("ngptot,nproma,perturbation,ksplit,target_b", [(163840, 128, "", 0, 0), (120000, 64, "warm+land+conv+rain+moist+tend", 40, 3),
-                                                                        (131071, 32, "sparse+warm+conv", 136, 12), (114688, 128, "hot+rain+moist+conv", 1, 1),
-                                                                        (60000, 32, "warm+land+conv+rain+moist+tend", 70, 4)])
+                                                                        (131071, 32, "sparse+warm+conv", 136, 12), (60000, 32, "hot+rain+moist+conv", 1, 1)])
 def test_persistent_schedule_is_bit_identical(built, input_data, ngptot, nproma, perturbation, ksplit, target_b):
     """cloudsc_b200_set_schedule(mode 1 / mode 2 / mode 3): persistent warps that take their tiles from a queue with the input
     ring kept full across tiles (2), one launch whose last blocks are the lower halves of tiles split at a cut (3), or warps
